@@ -1,0 +1,188 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The fixtures are what travels to the GPU box; nothing under
+tests/ reads /root/reference at test time.
+
+What is recorded
+  maps.npz         binarised occupancy (bit-packed, after the reference's flip+threshold,
+                   laser_models.py:398-404) + yaml metadata for every map the tests/bench use,
+                   the Shanghai centerline start poses, and the numpy-computed
+                   lookup tables (laser_models.py:379-381, base_classes.py:122-158).
+  scans.npz        noise-free ScanSimulator2D.scan(pose, None) at fixed poses.
+  rollout_*.npz    F110Env / Simulator rollouts: per-step fp64 states, flags, lap bookkeeping,
+                   and sub-sampled scans / flat observations.
+"""
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+warnings.filterwarnings('ignore')
+from ref_loader import REF_MAPS, REF_ROOT, fresh_statics, load_reference  # noqa: E402
+
+ns = load_reference()
+TMP = '/tmp/f110_golden_maps/'
+os.makedirs(TMP, exist_ok=True)
+
+
+def write_open_map():
+    """20 m x 20 m free square with a 3-pixel wall, used for the lap / GJK scenarios."""
+    from PIL import Image
+    img = np.full((400, 400), 254, np.uint8)
+    img[:3, :] = 0; img[-3:, :] = 0; img[:, :3] = 0; img[:, -3:] = 0
+    img[150:160, 300:360] = 0   # an interior block so the scan is not symmetric
+    Image.fromarray(img, mode='L').save(TMP + 'open_square.png')
+    with open(TMP + 'open_square.yaml', 'w') as f:
+        f.write("image: open_square.png\nresolution: 0.05\norigin: [-10.0, -10.0, 0.0]\nnegate: 0\n"
+                "occupied_thresh: 0.65\nfree_thresh: 0.196\n")
+
+
+def pack_map(map_dir, name, ext='.png'):
+    import yaml
+    from PIL import Image
+    img = np.array(Image.open(map_dir + name + ext).transpose(Image.FLIP_TOP_BOTTOM)).astype(np.float64)
+    free = img > 128.
+    meta = yaml.safe_load(open(map_dir + name + '.yaml'))
+    return {name + '__bits': np.packbits(free, axis=None), name + '__shape': np.array(free.shape),
+            name + '__resolution': np.float64(meta['resolution']),
+            name + '__origin': np.array(meta['origin'], np.float64)}
+
+
+def make_env(map_dir, name, num_agents=2, **kw):
+    fresh_statics(ns)
+    return ns.F110Env(map_dir=map_dir, map=name, map_ext='.png', num_agents=num_agents, **kw)
+
+
+def noise_digest(seed, steps, beams=1080):
+    rng = np.random.default_rng(seed)
+    h = hashlib.sha256()
+    for _ in range(steps):
+        h.update(rng.normal(0., 0.01, size=beams).tobytes())
+    return h.hexdigest()
+
+
+def record_env_rollout(env, poses, actions, every=50, seed=42):
+    """F110Env rollout; scans are the obs-dict fp64 scans (after noise and opponent ray-cast)."""
+    T, A = actions.shape[0], env.num_agents
+    rec = dict(poses=np.asarray(poses, np.float64), actions=actions, every=np.int64(every), seed=np.int64(seed))
+    st = np.zeros((T + 1, A, 7)); col = np.zeros((T + 1, A), np.uint8); term = np.zeros(T + 1, np.uint8)
+    tog = np.zeros((T + 1, A), np.int32); lt = np.zeros((T + 1, A)); lc = np.zeros((T + 1, A)); tm = np.zeros(T + 1)
+    ks = list(range(0, T + 1, every))
+    scans = np.zeros((len(ks), A, 1080)); obs = np.zeros((len(ks), 1088), np.float32)
+
+    def grab(k, o, done, info):
+        st[k] = np.stack([a.state for a in env.sim.agents])
+        col[k] = info['collisions']; term[k] = done; tog[k] = env.toggle_list
+        lt[k] = env.lap_times; lc[k] = env.lap_counts; tm[k] = info['time']
+        if k % every == 0:
+            scans[k // every] = np.stack(ns.F110Env.current_obs['scans']); obs[k // every] = o
+    o, info = env.reset(options=np.array(poses, np.float64))
+    grab(0, o, False, info)   # index 0 = state after reset (which already contains one zero-action step)
+    for t in range(T):
+        o, r, done, trunc, info = env.step(actions[t])
+        assert r == env.timestep and trunc is False
+        grab(t + 1, o, done, info)
+    rec.update(state=st, collisions=col, terminated=term, toggles=tog, lap_times=lt, lap_counts=lc, time=tm,
+               scans=scans, obs=obs, noise_sha256=np.array(noise_digest(seed, T + 1)))
+    return rec
+
+
+def record_sim_rollout(map_dir, name, pose, action, T, every=100, seed=42):
+    """C1: Simulator-level single agent (F110Env cannot pack a 1-agent observation, f110_env.py:554)."""
+    fresh_statics(ns)
+    params = make_env(map_dir, name).params
+    fresh_statics(ns)
+    sim = ns.Simulator(params, 1, seed, time_step=0.01, integrator=ns.Integrator.RK4)
+    sim.set_map(map_dir + name + '.yaml', '.png')
+    st = np.zeros((T, 7)); col = np.zeros(T, np.uint8); resets = np.zeros(T, np.uint8)
+    ks = list(range(0, T, every)); scans = np.zeros((len(ks), 1080))
+    pose = np.asarray(pose, np.float64)
+    sim.reset(pose[None])
+    act = np.asarray(action, np.float32)[None]
+    for t in range(T):
+        if t > 0 and col[t - 1]:
+            sim.reset(pose[None]); resets[t] = 1
+        obs = sim.step(act)
+        st[t] = sim.agents[0].state; col[t] = obs['collisions'][0]
+        if t % every == 0:
+            scans[t // every] = obs['scans'][0]
+    return dict(pose=pose, action=act, state=st, collisions=col, resets=resets, scans=scans,
+                every=np.int64(every), seed=np.int64(seed))
+
+
+def main():
+    write_open_map()
+    out = {}
+    out.update(pack_map(REF_MAPS, 'Shanghai_map'))
+    out.update(pack_map(REF_MAPS, 'straight_corridor'))
+    out.update(pack_map(TMP, 'open_square'))
+    cl = np.loadtxt(os.path.join(REF_ROOT, 'rl_training/maps/cenerlines/Shanghai_map.csv'), delimiter=',', comments='#')
+    nxt = np.roll(cl[:, :2], -1, axis=0)
+    yaw = np.arctan2(nxt[:, 1] - cl[:, 1], nxt[:, 0] - cl[:, 0])
+    out['Shanghai_map__centerline_poses'] = np.column_stack([cl[:, 0], cl[:, 1], yaw])
+    env = make_env(REF_MAPS, 'Shanghai_map')
+    R = ns.RaceCar
+    out.update(sines=R.scan_simulator.sines, cosines=R.scan_simulator.cosines, scan_angles=R.scan_angles,
+               beam_cosines=R.cosines, side_distances=R.side_distances)
+    np.savez_compressed(os.path.join(HERE, 'maps.npz'), **out)
+
+    # ---- noise-free scans
+    sc = {}
+    rng = np.random.default_rng(7)
+    poses = np.array([[0, 0, 0]] + [[rng.uniform(-70, 50), rng.uniform(-30, 60), rng.uniform(-4, 4)] for _ in range(23)])
+    poses[1] = [-200.0, 0.0, 1.0]     # outside the map
+    cp = out['Shanghai_map__centerline_poses']
+    poses[2:12] = cp[np.linspace(0, len(cp) - 1, 10).round().astype(int)]
+    sc['Shanghai_map__poses'] = poses
+    sc['Shanghai_map__scans'] = np.stack([R.scan_simulator.scan(p, None) for p in poses])
+    sc['Shanghai_map__dt_probe'] = np.array([R.scan_simulator.dt[-1, -1], R.scan_simulator.dt[0, 0], R.scan_simulator.dt.max(),
+                                             R.scan_simulator.dt.sum()])
+    env = make_env(REF_MAPS, 'straight_corridor')
+    poses = np.array([[0, 0, 0], [0.2, 5.0, 1.5], [-0.3, 40.0, -1.0], [0.0, 99.0, 1.57], [5.0, 5.0, 0.0], [0.1, -0.5, 3.0]])
+    sc['straight_corridor__poses'] = poses
+    sc['straight_corridor__scans'] = np.stack([R.scan_simulator.scan(p, None) for p in poses])
+    np.savez_compressed(os.path.join(HERE, 'scans.npz'), **sc)
+
+    # ---- S1: config C2, random actions on Shanghai
+    env = make_env(REF_MAPS, 'Shanghai_map')
+    acts = np.random.default_rng(0).uniform([-0.4189, 0], [0.4189, 20], size=(1000, 2, 2)).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, 'rollout_c2_shanghai.npz'),
+                        **record_env_rollout(env, [[0, 0, 0], [3.0, 0.5, 0]], acts))
+    # ---- S1b: constant action from the survey (ego TTC-terminates at step 221)
+    acts = np.tile(np.array([[0.05, 3.0], [0.0, 2.0]], np.float32), (400, 1, 1))
+    np.savez_compressed(os.path.join(HERE, 'rollout_const_shanghai.npz'),
+                        **record_env_rollout(env, [[0, 0, 0], [3.0, 0.5, 0]], acts))
+    # ---- S2: circles on the open map -> finish-zone toggles, lap counts, done by laps
+    env = make_env(TMP, 'open_square')
+    acts = np.tile(np.array([[0.4189, 1.5], [-0.4189, 2.0]], np.float32), (900, 1, 1))
+    np.savez_compressed(os.path.join(HERE, 'rollout_circles_open.npz'),
+                        **record_env_rollout(env, [[0, 0, 0.3], [2.0, -3.0, -1.0]], acts))
+    # ---- S3: head-on on the open map -> GJK collision flags + opponent ray-cast in the scans
+    acts = np.tile(np.array([[0.0, 3.0], [0.02, 2.5]], np.float32), (300, 1, 1))
+    np.savez_compressed(os.path.join(HERE, 'rollout_headon_open.npz'),
+                        **record_env_rollout(env, [[-4.0, 0, 0.0], [4.0, 0.15, np.pi - 0.01]], acts, every=10))
+    # ---- S3b: three agents, Euler integrator, lidar offset, non-default ego
+    env = make_env(TMP, 'open_square', num_agents=3, integrator=ns.Integrator.Euler, lidar_dist=0.275, ego_idx=1)
+    acts = np.random.default_rng(3).uniform([-0.4189, 0], [0.4189, 8], size=(300, 3, 2)).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, 'rollout_three_euler_open.npz'),
+                        **record_env_rollout(env, [[-2.0, 0, 0.0], [0.0, 0.3, 0.1], [1.2, 0.2, 3.0]], acts, every=25))
+    # ---- S4: rotated-origin corridor until the end wall (TTC)
+    env = make_env(REF_MAPS, 'straight_corridor')
+    acts = np.tile(np.array([[0.0, 8.0], [0.01, 6.0]], np.float32), (600, 1, 1))
+    np.savez_compressed(os.path.join(HERE, 'rollout_corridor.npz'),
+                        **record_env_rollout(env, [[0.0, 0.5, 1.5708], [0.3, 3.0, 1.5708]], acts))
+    # ---- S5: config C1, Simulator-level single agent with resets on collision
+    np.savez_compressed(os.path.join(HERE, 'rollout_c1_single.npz'),
+                        **record_sim_rollout(REF_MAPS, 'Shanghai_map', [0, 0, 0], [0.0, 2.0], 2000))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()
