@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched F110Env step path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--agents A] [--beams B]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the CPU arm: oracle port on all host cores
+
+Workload (config C3 of BASELINE.json / SURVEY 8d): E = 4096 single-agent envs per GPU on the Shanghai map
+(2000x2000 cells, 0.06505 m), 1080-beam 270-degree lidar, RK4 single-track dynamics, start poses spread over
+the centerline, iid uniform actions in the action-space bounds (pre-generated on the device, torch Philox seed
+1234), lidar noise from the on-device Philox stream, auto-reset to the start pose on the step after done.
+One "step" = one batched F110Env.step over all E envs of the rank.  Weak scaling: every rank owns E envs.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S_MIN, S_MAX, V_MIN, V_MAX = -0.4189, 0.4189, 0.0, 20.0   # ddpg_config.yaml:19-20 / f110_env.py action space
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (C3: 4096)")
+    ap.add_argument("--agents", type=int, default=1)
+    ap.add_argument("--beams", type=int, default=1080)
+    ap.add_argument("--map", default="Shanghai_map")
+    ap.add_argument("--map-upsample", type=int, default=1, help="nearest-neighbour upsample factor (C4 large maps)")
+    ap.add_argument("--cpu-envs", type=int, default=0, help="envs in the CPU sample (0 = auto)")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return ap.parse_args()
+
+
+def load_workload(args, num_envs, env_offset=0, total_envs=None):
+    """Map + start poses from the committed fixtures (nothing reads /root/reference at run time)."""
+    from tests import helpers as H
+    dt, res, origin = H.golden_map(args.map)
+    if args.map_upsample > 1:
+        # C4 "large maps": nearest-neighbour upsampling of the occupancy, resolution divided accordingly
+        from scipy.ndimage import distance_transform_edt
+        k = args.map_upsample
+        free = np.kron(dt > 0, np.ones((k, k), bool))
+        res = res / k
+        dt = res * distance_transform_edt(np.where(free, 255., 0.))
+    total = total_envs or num_envs
+    if args.map == "Shanghai_map":
+        cl = H.load('maps')['Shanghai_map__centerline_poses']
+        idx = np.linspace(0, len(cl) - 1, total).round().astype(int)[env_offset:env_offset + num_envs]
+        poses = np.zeros((num_envs, args.agents, 3))
+        for a in range(args.agents):
+            poses[:, a] = cl[(idx + 25 * a) % len(cl)]
+    else:
+        poses = np.zeros((num_envs, args.agents, 3))
+        poses[:, :, 0] = 1.0 * np.arange(args.agents)[None]
+    return (dt, res, origin), poses
+
+
+def action_stream(torch, steps, n, a, device, seed=1234):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand((steps, n, a, 2), generator=g, device=device, dtype=torch.float32)
+    lo = torch.tensor([S_MIN, V_MIN], device=device)
+    hi = torch.tensor([S_MAX, V_MAX], device=device)
+    return (lo + u * (hi - lo)).contiguous()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_arm(args, steps, warmup, envs=None, threads=None):
+    """The reference's CPU implementation of the path: the oracle port (the reference itself is Python/numba and
+    cannot travel to the GPU box), all host threads, a bounded sample of the same workload."""
+    from oracle.f110_oracle import Oracle
+    threads = threads or (os.cpu_count() or 1)
+    try:
+        threads = min(threads, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    n = envs or args.cpu_envs or max(64, 16 * threads)
+    n = min(n, args.envs)
+    map_arrays, poses = load_workload(args, n, 0, args.envs)
+    o = Oracle(n, args.agents, num_beams=args.beams, noise_std=0.01, seed=42, threads=threads)
+    o.set_map_arrays(*map_arrays)
+    rng = np.random.default_rng(1234)
+    acts = rng.uniform([S_MIN, V_MIN], [S_MAX, V_MAX], size=(steps + warmup, n, args.agents, 2)).astype(np.float32)
+    out = o.reset(poses)
+    term = out['terminated'].copy()
+    for k in range(warmup):
+        term = o.step(acts[k], reset_mask=term, reset_poses=poses, want_scans=False)['terminated'].copy()
+    look = 0
+    t0 = time.perf_counter()
+    for k in range(warmup, warmup + steps):
+        term = o.step(acts[k], reset_mask=term, reset_poses=poses, want_scans=False)['terminated'].copy()
+        look += o.last_lookups
+    el = time.perf_counter() - t0
+    return dict(value=n * steps / el, seconds=el, envs=n, steps=steps, threads=threads,
+                lookups_per_ray=look / float(n * steps * args.agents * args.beams))
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # size the sample so that W+K steps finish in a couple of minutes on any box
+    probe = cpu_arm(args, 2, 1)
+    per_step = probe['seconds'] / 2
+    budget = 60.0
+    envs = probe['envs']
+    if per_step * (args.steps + args.warmup) > budget:
+        envs = max(8, int(envs * budget / (per_step * (args.steps + args.warmup))))
+    r = cpu_arm(args, args.steps, args.warmup, envs=envs)
+    rays = r['value'] * args.agents * args.beams
+    line = {
+        "impl": "reference", "metric": "env-steps/s (1080-beam lidar)", "value": r['value'], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r['seconds'] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "rays_per_s": rays,
+        "config": workload_config(args, r['envs'], note="CPU arm: bounded sample of the same workload"),
+        "cpu_baseline": {"value": r['value'], "unit": "env-steps/s", "cores": r['threads'], "kind": "port",
+                         "sample": "%d envs x %d steps of the C3 workload (oracle/f110_oracle.c, pthreads)" % (r['envs'], r['steps'])},
+        "e2e": {"value": r['value'], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, envs_per_gpu, note=None):
+    c = {"workload": "C3: %d single-agent f110-v0 envs per GPU, %s, RK4 ST dynamics, %d-beam 4.7 rad lidar, uniform random "
+                     "actions, auto-reset on done" % (envs_per_gpu, args.map, args.beams),
+         "envs_per_gpu": envs_per_gpu, "agents": args.agents, "beams": args.beams, "map": args.map,
+         "map_upsample": args.map_upsample, "parallelism": "env-index sharding, no step-path collective"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+
+    from f110_gymnasium_ros2_jazzy_b200 import EpisodeStats, F110VecEnv, shard_range
+    E, A, B, K, W = args.envs, args.agents, args.beams, args.steps, args.warmup
+    total_envs = E * world
+    lo, hi = shard_range(total_envs, rank, world)
+    map_arrays, poses = load_workload(args, hi - lo, lo, total_envs)
+
+    def make_env(count=False):
+        env = F110VecEnv(E, num_agents=A, num_beams=B, seed=42 + rank, device=local, auto_reset=True,
+                         outputs=('obs', 'reward', 'terminated'), noise_std=0.01, count_lookups=count, map_arrays=map_arrays)
+        env.reset(poses)
+        return env
+
+    env = make_env()
+    acts = action_stream(torch, W + K, E, A, dev, seed=1234 + rank)
+    flush = None if args.no_flush else torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def run(env, first, n, per_step_events=None, flush_buf=None):
+        for k in range(first, first + n):
+            if flush_buf is not None:
+                flush_buf.fill_(k & 0xFF)          # evict L2 (252 MiB written) before every timed step
+            if per_step_events is not None:
+                per_step_events[k - first][0].record(stream)
+            env.step(acts[k])
+            if per_step_events is not None:
+                per_step_events[k - first][1].record(stream)
+
+    # ---- warm-up, then the timed region: K steps, device-timed per step so the flush is not counted
+    run(env, 0, W, None, flush)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = env.backend.kernel_launches
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    run(env, W, K, ev, flush)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.backend.kernel_launches - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(step_ms))
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    stats = EpisodeStats().reduce(env.backend.stats())   # the path's only collective, off the step path
+
+    value = total_envs * K / (dev_ms * 1e-3)
+    rays_per_s = value * A * B
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (lidar ray-march): kernel-only time via the library's event pairs
+        from f110_gymnasium_ros2_jazzy_b200 import _lib
+        lidar_ms, kern_ms = kernel_breakdown(env, acts, W, min(K, 50), flush, torch)
+        cenv = make_env(count=True)
+        for k in range(W + min(K, 50)):
+            cenv.step(acts[k])
+        looks, rays = cenv.backend.lookup_count()
+        cenv.close()
+        lbar = looks / max(rays, 1)
+        bytes_per_ray = 8.0 * lbar + 8.0                      # L-bar fp64 cells + fp64 range out
+        alg_bytes = bytes_per_ray * E * A * B                 # per launch
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / (lidar_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
+                    "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar,
+                    "bytes_per_ray": bytes_per_ray, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                    "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]}}
+        # ---- e2e through the host-buffer C ABI call (f110_step_host): pinned H2D actions, D2H obs/reward/terminated
+        e2e = None
+        if not args.no_e2e:
+            e2e = e2e_run(env, acts, W, K, E, A, B, torch)
+        # ---- CPU arm beside it
+        cpu = None
+        if not args.no_cpu_baseline:
+            c = cpu_arm(args, args.cpu_steps or 40, 3)
+            cpu = {"value": c['value'], "unit": "env-steps/s", "cores": c['threads'], "kind": "port",
+                   "sample": "%d envs x %d steps of the same workload, oracle/f110_oracle.c on %d threads (%.1f s)"
+                             % (c['envs'], c['steps'], c['threads'], c['seconds'])}
+        line = {
+            "metric": "env-steps/s (1080-beam lidar)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "rays_per_s": rays_per_s,
+            "config": dict(workload_config(args, E), total_envs=total_envs,
+                           l2="flushed between timed steps (252 MiB fill, outside the per-step events)" if flush is not None
+                           else "not flushed; per-step working set %.0f MiB" % ((E * A * B * 12 + map_arrays[0].nbytes) / 2**20),
+                           timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                           wall_ms_per_step_incl_flush=1e3 * t_wall / K),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "episode_stats": {k: stats[k] for k in ('episodes', 'ego_collisions', 'mean_episode_steps')},
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+def kernel_breakdown(env, acts, first, n, flush, torch):
+    """Average per-launch duration of each of the three kernels, CUDA events on the launch stream."""
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    import ctypes as C
+    L = env.backend.lib
+    _lib.check(L.f110_set_kernel_timing(env.backend.h, 1))
+    for k in range(first, first + n):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        env.step(acts[k])
+    torch.cuda.synchronize()
+    ms = (C.c_double * 3)()
+    cnt = C.c_int64(0)
+    _lib.check(L.f110_get_kernel_timing(env.backend.h, ms, C.byref(cnt)))
+    _lib.check(L.f110_set_kernel_timing(env.backend.h, 0))
+    per = [ms[i] / max(cnt.value, 1) for i in range(3)]
+    return per[1], per
+
+
+def e2e_run(env, acts, W, K, E, A, B, torch):
+    """Same metric through f110_step_host: every step copies the actions from pinned host memory to the device and
+    the observation / reward / terminated arrays back, inside the timed region."""
+    hacts = acts.cpu().pin_memory()
+    hout = env.backend.host_out(('obs', 'reward', 'terminated'))
+    hposes = env.start_poses.cpu().numpy()
+    term = hout['terminated'].numpy()
+    for k in range(min(W, 5)):
+        env.backend.step_host(hacts[k].numpy(), None, term, hposes, hout)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        env.backend.step_host(hacts[k].numpy(), None, term, hposes, hout)
+    el = time.perf_counter() - t0
+    h2d = E * A * 2 * 4 + E + E * A * 3 * 8
+    d2h = E * (B + 8) * 4 + E * 4 + E
+    return {"value": E * K / el, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * el / K, "api": "f110_step_host (C ABI, host buffers)", "n_gpus": 1}
+
+
+def load_traffic():
+    """dram bytes per lidar launch from the committed ncu capture, if one exists (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("lidar_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

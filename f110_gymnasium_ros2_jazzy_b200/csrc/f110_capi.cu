@@ -1,0 +1,420 @@
+// f110_capi.cu -- the C ABI declared in include/f110_b200.h.
+//
+// Owns the device arena (persistent simulation state + per-step scratch + lookup tables + map)
+// and sequences the three step kernels on the caller's stream.  No torch types, no hidden
+// allocation or synchronisation on the step path, no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "f110_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) return fail(F110_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct Arena {
+    // bump allocator over one cudaMalloc'd block, 256-byte aligned sub-allocations
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    template <typename T>
+    T* take(size_t n) {
+        used = (used + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+        used += n * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace
+
+struct F110Sim {
+    F110Config cfg;
+    SimConst c;
+    SimState st;
+    StepScratch sc;
+    MapView map;
+    bool map_set = false;
+    bool count_lookups = false;
+    // device memory
+    char* state_blob = nullptr;   size_t state_bytes = 0;    // checkpointable
+    char* scratch_blob = nullptr; size_t scratch_bytes = 0;
+    double* d_tables = nullptr;   // params[A][18], sim_params[18], sines, cosines, scan_angles, beam_cos, side_dist
+    double* d_map = nullptr;
+    // host-buffer path (f110_step_host)
+    cudaStream_t host_stream = nullptr;
+    char* io_blob = nullptr; size_t io_bytes = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   // 4 events per timed step
+};
+
+namespace {
+
+// lays out SimState inside `a`; with a.base == nullptr only measures
+void layout_state(Arena& a, SimState& st, int N, int NA) {
+    for (int k = 0; k < 7; ++k) st.x[k] = a.take<double>(NA);
+    st.steer_buf0 = a.take<double>(NA); st.steer_buf1 = a.take<double>(NA);
+    st.start_x = a.take<double>(NA); st.start_y = a.take<double>(NA); st.start_th = a.take<double>(NA);
+    st.lap_times = a.take<double>(NA); st.lap_counts = a.take<double>(NA);
+    st.time = a.take<double>(N); st.rot_c = a.take<double>(N); st.rot_s = a.take<double>(N);
+    st.steer_cnt = a.take<int32_t>(NA); st.toggles = a.take<int32_t>(NA);
+    st.step_count = a.take<uint32_t>(N);
+    st.near_start = a.take<uint8_t>(NA); st.collisions = a.take<uint8_t>(NA);
+}
+
+void layout_scratch(Arena& a, StepScratch& sc, int NA, int B) {
+    sc.scan_x = a.take<double>(NA); sc.scan_y = a.take<double>(NA); sc.pre_yaw = a.take<double>(NA);
+    sc.theta0 = a.take<double>(NA);
+    sc.ttc_hit = a.take<int32_t>(NA);
+    sc.lookups = a.take<unsigned long long>(2);
+    sc.stats = a.take<double>(F110_NUM_STATS);
+    sc.scan = a.take<double>((size_t)NA * B);
+}
+
+struct Guard {   // selects the handle's device for the duration of a call
+    int prev = -1;
+    bool ok = true;
+    explicit Guard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_step_io(const F110Sim* sim, const F110StepIO* io) {
+    if (!sim || !io) return fail(F110_ERR_INVALID, "null handle or io");
+    if (!sim->map_set) return fail(F110_ERR_MAP_NOT_SET, "Map is not set for scan simulator.");
+    if (io->reset_mask && !io->reset_poses) return fail(F110_ERR_INVALID, "reset_mask given without reset_poses");
+    return F110_OK;
+}
+
+int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
+    cudaEvent_t e[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (sim->timing) {
+        for (int i = 0; i < 4; ++i) { CUDA_TRY(cudaEventCreate(&e[i])); sim->tev.push_back(e[i]); }
+        CUDA_TRY(cudaEventRecord(e[0], s));
+    }
+    launch_dynamics(sim->c, sim->st, sim->sc, io, s);
+    if (sim->timing) CUDA_TRY(cudaEventRecord(e[1], s));
+    launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, s);
+    if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
+    launch_post(sim->c, sim->st, sim->sc, io, s);
+    if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
+    sim->launches += 3;
+    CUDA_TRY(cudaPeekAtLastError());
+    return F110_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* f110_last_error(void) { return g_err.c_str(); }
+int f110_abi_version(void) { return F110_ABI_VERSION; }
+
+int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
+    if (!cfg || !params || !out) return fail(F110_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != F110_ABI_VERSION) return fail(F110_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, F110_ABI_VERSION);
+    if (cfg->num_envs < 1 || cfg->num_agents < 1 || cfg->num_agents > F110_MAX_AGENTS || cfg->num_beams < 2 || cfg->theta_dis < 2)
+        return fail(F110_ERR_INVALID, "need num_envs >= 1, 1 <= num_agents <= %d, num_beams >= 2, theta_dis >= 2", F110_MAX_AGENTS);
+    if (cfg->ego_idx < 0 || cfg->ego_idx >= cfg->num_agents) return fail(F110_ERR_INDEX, "ego_idx out of range");
+    if (cfg->integrator != F110_INTEGRATOR_RK4 && cfg->integrator != F110_INTEGRATOR_EULER)
+        return fail(F110_ERR_INTEGRATOR, "Invalid Integrator Specified. Please choose RK4 or Euler");
+    if ((double)cfg->num_envs * cfg->num_agents * cfg->num_beams >= 2147483648.0)
+        return fail(F110_ERR_INVALID, "num_envs*num_agents*num_beams must be < 2^31 per handle; shard across handles/GPUs");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(F110_ERR_NO_DEVICE, "no CUDA device visible: libf110_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(F110_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+    Guard g(cfg->device);
+    if (!g.ok) return fail(F110_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+
+    F110Sim* sim = new F110Sim();
+    sim->cfg = *cfg;
+    const int N = cfg->num_envs, A = cfg->num_agents, B = cfg->num_beams, NA = N * A;
+    sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
+
+    Arena measure;
+    layout_state(measure, sim->st, N, NA);
+    sim->state_bytes = (measure.used + 255) & ~size_t(255);
+    Arena measure2;
+    layout_scratch(measure2, sim->sc, NA, B);
+    sim->scratch_bytes = (measure2.used + 255) & ~size_t(255);
+    const size_t ntab = (size_t)A * F110_NUM_PARAMS + F110_NUM_PARAMS + 2 * (size_t)cfg->theta_dis + 3 * (size_t)B;
+
+    cudaError_t e = cudaMalloc(&sim->state_blob, sim->state_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&sim->scratch_blob, sim->scratch_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&sim->d_tables, ntab * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(sim->state_blob, 0, sim->state_bytes);
+    if (e == cudaSuccess) e = cudaMemset(sim->scratch_blob, 0, sim->scratch_bytes);
+    if (e == cudaSuccess) e = cudaMemset(sim->d_tables, 0, ntab * sizeof(double));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sim->host_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        fail(F110_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+        f110_destroy(sim);
+        return F110_ERR_CUDA;
+    }
+    Arena a; a.base = sim->state_blob; layout_state(a, sim->st, N, NA);
+    Arena b; b.base = sim->scratch_blob; layout_scratch(b, sim->sc, NA, B);
+
+    double* t = sim->d_tables;
+    SimConst& c = sim->c;
+    c.N = N; c.A = A; c.B = B; c.NA = NA;
+    c.theta_dis = cfg->theta_dis; c.integrator = cfg->integrator; c.ego = cfg->ego_idx;
+    c.fov = cfg->fov; c.eps = cfg->eps; c.max_range = cfg->max_range; c.timestep = cfg->timestep;
+    c.lidar_dist = cfg->lidar_dist; c.ttc_thresh = cfg->ttc_thresh; c.noise_std = cfg->noise_std;
+    c.lidar_max = (float)cfg->lidar_max; c.seed = cfg->seed;
+    // ScanSimulator2D.__init__ laser_models.py:367-368
+    const double angle_increment = cfg->fov / (B - 1);
+    c.theta_inc = cfg->theta_dis * angle_increment / (2. * F110_PI);
+    c.params = t; t += (size_t)A * F110_NUM_PARAMS;
+    c.sim_params = t; t += F110_NUM_PARAMS;
+    c.sines = t; t += cfg->theta_dis;
+    c.cosines = t; t += cfg->theta_dis;
+    c.scan_angles = t; t += B;
+    c.beam_cos = t; t += B;
+    c.side_dist = t; t += B;
+
+    std::vector<double> hp((size_t)(A + 1) * F110_NUM_PARAMS);
+    for (int i = 0; i <= A; ++i) memcpy(&hp[(size_t)i * F110_NUM_PARAMS], params, sizeof(double) * F110_NUM_PARAMS);
+    e = cudaMemcpy(sim->d_tables, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    // near_start is True at construction (f110_env.py:213)
+    if (e == cudaSuccess) e = cudaMemset(sim->st.near_start, 1, NA);
+    if (e != cudaSuccess) {
+        fail(F110_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+        f110_destroy(sim);
+        return F110_ERR_CUDA;
+    }
+    memset(&sim->map, 0, sizeof(sim->map));
+    *out = sim;
+    return F110_OK;
+}
+
+void f110_destroy(F110Sim* sim) {
+    if (!sim) return;
+    Guard g(sim->cfg.device);
+    if (sim->host_stream) { cudaStreamSynchronize(sim->host_stream); cudaStreamDestroy(sim->host_stream); }
+    cudaFree(sim->state_blob); cudaFree(sim->scratch_blob); cudaFree(sim->d_tables); cudaFree(sim->d_map);
+    cudaFree(sim->io_blob);
+    for (cudaEvent_t e : sim->tev) cudaEventDestroy(e);
+    delete sim;
+}
+
+int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
+                 double orig_x, double orig_y, double orig_cos, double orig_sin) {
+    if (!sim || !dt || height < 1 || width < 1 || !(resolution > 0)) return fail(F110_ERR_INVALID, "bad map arguments");
+    if ((double)height * width >= 2147483648.0) return fail(F110_ERR_INVALID, "map too large for 32-bit cell indices");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    double* d = nullptr;
+    const size_t bytes = (size_t)height * width * sizeof(double);
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpy(d, dt, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return fail(F110_ERR_CUDA, "map upload: %s", cudaGetErrorString(e)); }
+    cudaFree(sim->d_map);
+    sim->d_map = d;
+    MapView& m = sim->map;
+    m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
+    m.res = resolution; m.inv_res = 1.0 / resolution;
+    m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
+    m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
+    sim->map_set = true;
+    return F110_OK;
+}
+
+int f110_set_tables(F110Sim* sim, const double* sines, const double* cosines) {
+    if (!sim || !sines || !cosines) return fail(F110_ERR_INVALID, "null argument");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = sizeof(double) * sim->cfg.theta_dis;
+    CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.sines), sines, n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.cosines), cosines, n, cudaMemcpyHostToDevice));
+    return F110_OK;
+}
+
+int f110_set_beam_tables(F110Sim* sim, const double* scan_angles, const double* beam_cosines, const double* side_distances) {
+    if (!sim || !scan_angles || !beam_cosines || !side_distances) return fail(F110_ERR_INVALID, "null argument");
+    for (int i = 1; i < sim->cfg.num_beams; ++i)
+        if (!(scan_angles[i] > scan_angles[i - 1])) return fail(F110_ERR_INVALID, "scan_angles must be strictly increasing");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = sizeof(double) * sim->cfg.num_beams;
+    CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.scan_angles), scan_angles, n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.beam_cos), beam_cosines, n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.side_dist), side_distances, n, cudaMemcpyHostToDevice));
+    return F110_OK;
+}
+
+int f110_set_params(F110Sim* sim, const double* params, int32_t agent_idx) {
+    if (!sim || !params) return fail(F110_ERR_INVALID, "null argument");
+    if (agent_idx >= sim->cfg.num_agents) return fail(F110_ERR_INDEX, "Index given is out of bounds for list of agents.");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    double* base = const_cast<double*>(sim->c.params);
+    for (int a = 0; a < sim->cfg.num_agents; ++a)
+        if (agent_idx < 0 || a == agent_idx)
+            CUDA_TRY(cudaMemcpy(base + (size_t)a * F110_NUM_PARAMS, params, sizeof(double) * F110_NUM_PARAMS, cudaMemcpyHostToDevice));
+    return F110_OK;
+}
+
+int f110_sim_reset(F110Sim* sim, const double* poses, int32_t num_poses, const uint8_t* env_mask, void* stream) {
+    if (!sim || !poses) return fail(F110_ERR_INVALID, "null argument");
+    if (num_poses != sim->cfg.num_agents) return fail(F110_ERR_POSE_COUNT, "Number of poses for reset does not match number of agents.");
+    Guard g(sim->cfg.device);
+    launch_sim_reset(sim->c, sim->st, poses, env_mask, (cudaStream_t)stream);
+    sim->launches += 1;
+    CUDA_TRY(cudaPeekAtLastError());
+    return F110_OK;
+}
+
+int f110_step(F110Sim* sim, const F110StepIO* io, void* stream) {
+    const int rc = check_step_io(sim, io);
+    if (rc != F110_OK) return rc;
+    Guard g(sim->cfg.device);
+    return run_step(sim, *io, (cudaStream_t)stream);
+}
+
+int f110_step_host(F110Sim* sim, const F110StepIO* hio) {
+    const int rc = check_step_io(sim, hio);
+    if (rc != F110_OK) return rc;
+    Guard g(sim->cfg.device);
+    const size_t N = sim->c.N, NA = sim->c.NA, B = sim->c.B;
+    if (!sim->io_blob) {
+        // device mirrors of every field of F110StepIO (worst case), allocated on first use
+        Arena m;
+        m.take<double>(NA * 2); m.take<double>(NA * B); m.take<uint8_t>(N); m.take<double>(NA * 3); m.take<uint8_t>(N);
+        m.take<float>(N * (B + 8)); m.take<float>(N); m.take<uint8_t>(N); m.take<double>(NA * B); m.take<float>(NA * B);
+        m.take<double>(NA * 7); m.take<uint8_t>(NA); m.take<int32_t>(NA); m.take<double>(NA); m.take<double>(NA); m.take<double>(N);
+        sim->io_bytes = (m.used + 255) & ~size_t(255);
+        CUDA_TRY(cudaMalloc(&sim->io_blob, sim->io_bytes));
+    }
+    Arena a; a.base = sim->io_blob;
+    double* d_act = a.take<double>(NA * 2); double* d_noise = a.take<double>(NA * B); uint8_t* d_rmask = a.take<uint8_t>(N);
+    double* d_rposes = a.take<double>(NA * 3); uint8_t* d_amask = a.take<uint8_t>(N);
+    float* d_obs = a.take<float>(N * (B + 8)); float* d_rew = a.take<float>(N); uint8_t* d_term = a.take<uint8_t>(N);
+    double* d_s64 = a.take<double>(NA * B); float* d_s32 = a.take<float>(NA * B); double* d_state = a.take<double>(NA * 7);
+    uint8_t* d_col = a.take<uint8_t>(NA); int32_t* d_tog = a.take<int32_t>(NA); double* d_lt = a.take<double>(NA);
+    double* d_lc = a.take<double>(NA); double* d_time = a.take<double>(N);
+
+    cudaStream_t s = sim->host_stream;
+    F110StepIO d = *hio;
+#define H2D(field, dptr, bytes)                                                                   \
+    if (hio->field) { CUDA_TRY(cudaMemcpyAsync(dptr, hio->field, bytes, cudaMemcpyHostToDevice, s)); d.field = dptr; }
+    H2D(actions, d_act, NA * 2 * (hio->actions_f64 ? sizeof(double) : sizeof(float)))
+    H2D(noise, d_noise, NA * B * sizeof(double))
+    H2D(reset_mask, d_rmask, N)
+    H2D(reset_poses, d_rposes, NA * 3 * sizeof(double))
+    H2D(active_mask, d_amask, N)
+#undef H2D
+    d.obs = hio->obs ? d_obs : nullptr; d.reward = hio->reward ? d_rew : nullptr; d.terminated = hio->terminated ? d_term : nullptr;
+    d.scans_f64 = hio->scans_f64 ? d_s64 : nullptr; d.scans_f32 = hio->scans_f32 ? d_s32 : nullptr;
+    d.state = hio->state ? d_state : nullptr; d.collisions = hio->collisions ? d_col : nullptr;
+    d.toggles = hio->toggles ? d_tog : nullptr; d.lap_times = hio->lap_times ? d_lt : nullptr;
+    d.lap_counts = hio->lap_counts ? d_lc : nullptr; d.time = hio->time ? d_time : nullptr;
+    const int rc2 = run_step(sim, d, s);
+    if (rc2 != F110_OK) return rc2;
+#define D2H(field, dptr, bytes) \
+    if (hio->field) CUDA_TRY(cudaMemcpyAsync(hio->field, dptr, bytes, cudaMemcpyDeviceToHost, s));
+    D2H(obs, d_obs, N * (B + 8) * sizeof(float))
+    D2H(reward, d_rew, N * sizeof(float))
+    D2H(terminated, d_term, N)
+    D2H(scans_f64, d_s64, NA * B * sizeof(double))
+    D2H(scans_f32, d_s32, NA * B * sizeof(float))
+    D2H(state, d_state, NA * 7 * sizeof(double))
+    D2H(collisions, d_col, NA)
+    D2H(toggles, d_tog, NA * sizeof(int32_t))
+    D2H(lap_times, d_lt, NA * sizeof(double))
+    D2H(lap_counts, d_lc, NA * sizeof(double))
+    D2H(time, d_time, N * sizeof(double))
+#undef D2H
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return F110_OK;
+}
+
+int64_t f110_state_nbytes(const F110Sim* sim) { return sim ? (int64_t)sim->state_bytes : 0; }
+
+int f110_get_state(F110Sim* sim, void* dst, void* stream) {
+    if (!sim || !dst) return fail(F110_ERR_INVALID, "null argument");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaMemcpyAsync(dst, sim->state_blob, sim->state_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return F110_OK;
+}
+
+int f110_set_state(F110Sim* sim, const void* src, void* stream) {
+    if (!sim || !src) return fail(F110_ERR_INVALID, "null argument");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaMemcpyAsync(sim->state_blob, src, sim->state_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return F110_OK;
+}
+
+int f110_get_stats(F110Sim* sim, double* out, int32_t reset, void* stream) {
+    if (!sim || !out) return fail(F110_ERR_INVALID, "null argument");
+    Guard g(sim->cfg.device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(out, sim->sc.stats, sizeof(double) * F110_NUM_STATS, cudaMemcpyDeviceToDevice, s));
+    if (reset) CUDA_TRY(cudaMemsetAsync(sim->sc.stats, 0, sizeof(double) * F110_NUM_STATS, s));
+    return F110_OK;
+}
+
+int f110_get_lookup_count(F110Sim* sim, uint64_t* lookups, uint64_t* rays) {
+    if (!sim || !lookups || !rays) return fail(F110_ERR_INVALID, "null argument");
+    if (!sim->count_lookups) return fail(F110_ERR_INVALID, "handle was created without F110_FLAG_COUNT_LOOKUPS");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpy(h, sim->sc.lookups, sizeof(h), cudaMemcpyDeviceToHost));
+    *lookups = h[0]; *rays = h[1];
+    return F110_OK;
+}
+
+int f110_set_kernel_timing(F110Sim* sim, int32_t enable) {
+    if (!sim) return fail(F110_ERR_INVALID, "null handle");
+    sim->timing = enable != 0;
+    return F110_OK;
+}
+
+int f110_get_kernel_timing(F110Sim* sim, double* ms3, int64_t* steps) {
+    if (!sim || !ms3 || !steps) return fail(F110_ERR_INVALID, "null argument");
+    Guard g(sim->cfg.device);
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    *steps = (int64_t)(sim->tev.size() / 4);
+    for (size_t i = 0; i + 3 < sim->tev.size(); i += 4) {
+        CUDA_TRY(cudaEventSynchronize(sim->tev[i + 3]));
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, sim->tev[i + k], sim->tev[i + k + 1]));
+            ms3[k] += ms;
+        }
+    }
+    for (cudaEvent_t e : sim->tev) cudaEventDestroy(e);
+    sim->tev.clear();
+    return F110_OK;
+}
+
+int64_t f110_kernel_launches(const F110Sim* sim) { return sim ? sim->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,715 @@
+// f110_kernels.cu -- the three sm_100a kernels of one batched F110Env step.
+//
+//   K1 dynamics_kernel : one thread per vehicle.  Steering-delay FIFO, bang-bang/P controller,
+//                        fp64 single-track RK4 (or Euler), post clamps, lidar pose.
+//                        (RaceCar.update_pose, base_classes.py:256-422)
+//   K2 lidar_kernel    : one thread per beam, flat over all N*A*B rays.  Ray-march over the
+//                        distance transform, + noise, per-beam iTTC test.
+//                        (get_scan/trace_ray laser_models.py:106-186, scan :429-454,
+//                         check_ttc_jit :188-217)
+//   K3 post_kernel     : one CTA per env.  iTTC state zeroing, GJK over all pairs, opponent
+//                        ray-cast, finish-zone/lap bookkeeping, done, observation packing.
+//                        (base_classes.py:229-254,206-227,549-563,592-602; f110_env.py:310-352,552-602)
+//
+// Reference paths are relative to f110_gymnasium/gym/f110_gym/envs/.
+// Compile with -fmad=false: the operator order below is the reference's, without contraction.
+#include "f110_kernels.cuh"
+
+#include <math.h>
+
+namespace {
+
+enum { P_MU = F110_P_MU, P_CSF = F110_P_C_SF, P_CSR = F110_P_C_SR, P_LF = F110_P_LF, P_LR = F110_P_LR,
+       P_H = F110_P_H, P_M = F110_P_M, P_I = F110_P_I, P_SMIN = F110_P_S_MIN, P_SMAX = F110_P_S_MAX,
+       P_SVMIN = F110_P_SV_MIN, P_SVMAX = F110_P_SV_MAX, P_VSWITCH = F110_P_V_SWITCH, P_AMAX = F110_P_A_MAX,
+       P_VMIN = F110_P_V_MIN, P_VMAX = F110_P_V_MAX, P_WIDTH = F110_P_WIDTH, P_LENGTH = F110_P_LENGTH };
+
+// ---------------------------------------------------------------- numpy scalar semantics
+
+// np.clip(x, lo, hi) = min(max(x, lo), hi), NaN propagating
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+    x = (x < lo) ? lo : x;
+    x = (x > hi) ? hi : x;
+    return x;
+}
+
+// Python float `a % b` for b > 0 (floored modulo)
+__device__ __forceinline__ double floored_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if (m < 0.0) m += b;
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
+
+__device__ __forceinline__ double wrap_angle(double a) {  // base_classes.py:408, f110_env.py:548-550
+    return floored_mod(a + F110_PI, 2 * F110_PI) - F110_PI;
+}
+
+// ---------------------------------------------------------------- vehicle model
+
+struct VehParams {
+    double mu, C_Sf, C_Sr, lf, lr, h, m, I, s_min, s_max, sv_min, sv_max, v_switch, a_max, v_min, v_max;
+};
+
+__device__ __forceinline__ VehParams load_params(const double* __restrict__ p) {
+    VehParams v;
+    v.mu = __ldg(p + P_MU); v.C_Sf = __ldg(p + P_CSF); v.C_Sr = __ldg(p + P_CSR); v.lf = __ldg(p + P_LF);
+    v.lr = __ldg(p + P_LR); v.h = __ldg(p + P_H); v.m = __ldg(p + P_M); v.I = __ldg(p + P_I);
+    v.s_min = __ldg(p + P_SMIN); v.s_max = __ldg(p + P_SMAX); v.sv_min = __ldg(p + P_SVMIN);
+    v.sv_max = __ldg(p + P_SVMAX); v.v_switch = __ldg(p + P_VSWITCH); v.a_max = __ldg(p + P_AMAX);
+    v.v_min = __ldg(p + P_VMIN); v.v_max = __ldg(p + P_VMAX);
+    return v;
+}
+
+// accl_constraints, dynamic_models.py:29-60
+__device__ __forceinline__ double accl_constraints(double vel, double accl, const VehParams& p) {
+    double pos_limit = (vel > p.v_switch) ? p.a_max * p.v_switch / vel : p.a_max;
+    if ((vel <= p.v_min && accl <= 0) || (vel >= p.v_max && accl >= 0)) accl = 0.;
+    else if (accl <= -p.a_max) accl = -p.a_max;
+    else if (accl >= pos_limit) accl = pos_limit;
+    return accl;
+}
+
+// steering_constraint, dynamic_models.py:62-87
+__device__ __forceinline__ double steering_constraint(double sa, double sv, const VehParams& p) {
+    if ((sa <= p.s_min && sv <= 0) || (sa >= p.s_max && sv >= 0)) sv = 0.;
+    else if (sv <= p.sv_min) sv = p.sv_min;
+    else if (sv >= p.sv_max) sv = p.sv_max;
+    return sv;
+}
+
+// vehicle_dynamics_st (with the embedded vehicle_dynamics_ks branch), dynamic_models.py:90-176
+__device__ __forceinline__ void vehicle_dynamics_st(const double (&x)[7], double u_sv, double u_accl,
+                                                    const VehParams& p, double (&f)[7]) {
+    const double g = 9.81;
+    const double u0 = steering_constraint(x[2], u_sv, p);
+    const double u1 = accl_constraints(x[3], u_accl, p);
+    if (fabs(x[3]) < 0.5) {
+        // kinematic branch :152-160; vehicle_dynamics_ks re-applies the (idempotent) constraints :112
+        const double lwb = p.lf + p.lr;
+        const double k0 = steering_constraint(x[2], u0, p);
+        const double k1 = accl_constraints(x[3], u1, p);
+        double s4, c4;
+        sincos(x[4], &s4, &c4);
+        const double t2 = tan(x[2]);
+        const double c2 = cos(x[2]);
+        f[0] = x[3] * c4;
+        f[1] = x[3] * s4;
+        f[2] = k0;
+        f[3] = k1;
+        f[4] = x[3] / lwb * t2;
+        f[5] = u1 / lwb * t2 + x[3] / (lwb * (c2 * c2)) * u0;
+        f[6] = 0.0;
+    } else {
+        double sb, cb;
+        sincos(x[6] + x[4], &sb, &cb);
+        const double lrlf = p.lr + p.lf;
+        const double glr = g * p.lr - u1 * p.h;   // (g*lr - u[1]*h)
+        const double glf = g * p.lf + u1 * p.h;   // (g*lf + u[1]*h)
+        f[0] = x[3] * cb;
+        f[1] = x[3] * sb;
+        f[2] = u0;
+        f[3] = u1;
+        f[4] = x[5];
+        f[5] = -p.mu * p.m / (x[3] * p.I * lrlf) * (p.lf * p.lf * p.C_Sf * glr + p.lr * p.lr * p.C_Sr * glf) * x[5]
+             + p.mu * p.m / (p.I * lrlf) * (p.lr * p.C_Sr * glf - p.lf * p.C_Sf * glr) * x[6]
+             + p.mu * p.m / (p.I * lrlf) * p.lf * p.C_Sf * glr * x[2];
+        f[6] = (p.mu / (x[3] * x[3] * lrlf) * (p.C_Sr * glf * p.lr - p.C_Sf * glr * p.lf) - 1) * x[5]
+             - p.mu / (x[3] * lrlf) * (p.C_Sr * glf + p.C_Sf * glr) * x[6]
+             + p.mu / (x[3] * lrlf) * (p.C_Sf * glr) * x[2];
+    }
+}
+
+// pid, dynamic_models.py:178-221
+__device__ __forceinline__ void pid(double speed, double steer, double cur_speed, double cur_steer,
+                                    const VehParams& p, double& accl, double& sv) {
+    const double steer_diff = steer - cur_steer;
+    if (fabs(steer_diff) > 1e-4) sv = (steer_diff / fabs(steer_diff)) * p.sv_max;
+    else sv = 0.0;
+    const double vel_diff = speed - cur_speed;
+    double kp;
+    if (cur_speed > 0.) {
+        kp = (vel_diff > 0) ? 10.0 * p.a_max / p.v_max : 10.0 * p.a_max / (-p.v_min);
+    } else {
+        kp = (vel_diff > 0) ? 2.0 * p.a_max / p.v_max : 2.0 * p.a_max / (-p.v_min);
+    }
+    accl = kp * vel_diff;
+}
+
+// ---------------------------------------------------------------- K1: dynamics
+
+__global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.NA) return;
+    const int env = s / c.A;
+    const int a = s - env * c.A;
+    if (io.active_mask && !io.active_mask[env]) return;
+    const bool rst = io.reset_mask && io.reset_mask[env];
+
+    double x[7];
+    double b0, b1;
+    int cnt;
+    if (rst) {
+        // F110Env.reset bookkeeping (f110_env.py:440-451) + RaceCar.reset (base_classes.py:183-204)
+        const double* ps = io.reset_poses + (size_t)s * 3;
+        const double px = ps[0], py = ps[1], pth = ps[2];
+        x[0] = px; x[1] = py; x[2] = 0.; x[3] = 0.; x[4] = pth; x[5] = 0.; x[6] = 0.;
+        b0 = b1 = 0.;
+        cnt = 0;
+        st.start_x[s] = px; st.start_y[s] = py; st.start_th[s] = pth;
+        st.near_start[s] = 1;
+        st.toggles[s] = 0;
+        st.collisions[s] = 0;
+        if (a == c.ego) {
+            const double th = -pth;
+            st.rot_c[env] = cos(th);
+            st.rot_s[env] = sin(th);
+        }
+        if (a == 0) { st.time[env] = 0.0; st.step_count[env] = 0u; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) x[k] = st.x[k][s];
+        b0 = st.steer_buf0[s]; b1 = st.steer_buf1[s];
+        cnt = st.steer_cnt[s];
+        if (a == 0) st.step_count[env] += 1u;
+    }
+
+    double raw_steer = 0., speed = 0.;
+    if (!rst && io.actions) {   // the reset's own step uses a zero action (f110_env.py:457-458)
+        if (io.actions_f64) {
+            const double2 v = reinterpret_cast<const double2*>(io.actions)[s];
+            raw_steer = v.x; speed = v.y;
+        } else {
+            const float2 v = reinterpret_cast<const float2*>(io.actions)[s];
+            raw_steer = (double)v.x; speed = (double)v.y;
+        }
+    }
+
+    // steering delay FIFO, base_classes.py:270-278
+    double steer;
+    if (cnt < 2) { steer = 0.; cnt += 1; }
+    else steer = b1;
+    b1 = b0; b0 = raw_steer;
+
+    const VehParams p = load_params(c.params + a * F110_NUM_PARAMS);
+    double accl, sv;
+    pid(speed, steer, x[3], x[2], p, accl, sv);
+    sv = clipd(sv, p.sv_min, p.sv_max);         // :283
+    accl = clipd(accl, -p.a_max, p.a_max);      // :284
+
+    const double dt = c.timestep;
+    if (c.integrator == F110_INTEGRATOR_RK4) {  // :285-374
+        double k1[7], k2[7], k3[7], k4[7], xs[7];
+        vehicle_dynamics_st(x, sv, accl, p, k1);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * (k1[i] / 2);
+        vehicle_dynamics_st(xs, sv, accl, p, k2);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * (k2[i] / 2);
+        vehicle_dynamics_st(xs, sv, accl, p, k3);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * k3[i];
+        vehicle_dynamics_st(xs, sv, accl, p, k4);
+        const double w = dt * (1.0 / 6.0);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = x[i] + w * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    } else {                                    // Euler :376-396
+        double f[7];
+        vehicle_dynamics_st(x, sv, accl, p, f);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = x[i] + dt * f[i];
+    }
+
+    // post clamps :400-417
+    x[2] = clipd(x[2], p.s_min, p.s_max);
+    x[3] = clipd(x[3], p.v_min, p.v_max);
+    x[4] = wrap_angle(x[4]);
+    const double YAW_RATE_CAP = 10.0;
+    if (x[5] != x[5]) x[5] = 0.0;
+    else if (isinf(x[5])) x[5] = x[5] > 0 ? YAW_RATE_CAP : -YAW_RATE_CAP;
+    x[5] = clipd(x[5], -YAW_RATE_CAP, YAW_RATE_CAP);
+    const double SLIP_CAP = 60 * (F110_PI / 180.0);
+    if (x[6] != x[6]) x[6] = 0.0;
+    x[6] = clipd(x[6], -SLIP_CAP, SLIP_CAP);
+
+#pragma unroll
+    for (int k = 0; k < 7; ++k) st.x[k][s] = x[k];
+    st.steer_buf0[s] = b0; st.steer_buf1[s] = b1;
+    st.steer_cnt[s] = cnt;
+
+    // lidar pose :420-422 and the wrapped index of beam 0 (laser_models.py:167-172)
+    double sx = x[0], sy = x[1];
+    if (c.lidar_dist != 0.0) {
+        double sn, cs;
+        sincos(x[4], &sn, &cs);
+        sx = x[0] + c.lidar_dist * cs;
+        sy = x[1] + c.lidar_dist * sn;
+    }
+    sc.scan_x[s] = sx; sc.scan_y[s] = sy; sc.pre_yaw[s] = x[4];
+    double ti = (double)c.theta_dis * (x[4] - c.fov / 2.) / (2. * F110_PI);
+    ti = fmod(ti, (double)c.theta_dis);
+    while (ti < 0) ti += (double)c.theta_dis;
+    sc.theta0[s] = ti;
+    sc.ttc_hit[s] = 0;
+}
+
+// Simulator.reset alone (base_classes.py:627-643): poses only, no step, env bookkeeping untouched
+__global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restrict__ poses, const uint8_t* __restrict__ mask) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.NA) return;
+    const int env = s / c.A;
+    if (mask && !mask[env]) return;
+    const double* ps = poses + (size_t)s * 3;
+    st.x[0][s] = ps[0]; st.x[1][s] = ps[1]; st.x[2][s] = 0.; st.x[3][s] = 0.;
+    st.x[4][s] = ps[2]; st.x[5][s] = 0.; st.x[6][s] = 0.;
+    st.steer_buf0[s] = 0.; st.steer_buf1[s] = 0.; st.steer_cnt[s] = 0;
+    if (s - env * c.A == 0) st.step_count[env] = 0u;
+}
+
+// ---------------------------------------------------------------- K2: lidar
+
+// xy_2_rc + distance_transform, laser_models.py:55-104
+__device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y) {
+    const double x_trans = x - m.ox;
+    const double y_trans = y - m.oy;
+    const double x_rot = x_trans * m.oc + y_trans * m.os;
+    const double y_rot = -x_trans * m.os + y_trans * m.oc;
+    int idx;
+    if (x_rot < 0 || x_rot >= m.wres || y_rot < 0 || y_rot >= m.hres) {
+        idx = m.last;   // (r, c) = (-1, -1) wraps to dt[H-1][W-1]
+    } else {
+        const int col = (int)(x_rot / m.res);
+        const int row = (int)(y_rot / m.res);
+        idx = row * m.W + col;
+    }
+    return __ldg(m.dt + idx);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: no per-ray generator state in HBM
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float gaussian_from_bits(uint32_t a, uint32_t b) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
+    const unsigned total = (unsigned)c.NA * (unsigned)c.B;
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nlook = 0;
+    bool live = r < total;
+    unsigned s = 0, i = 0;
+    if (live) {
+        s = r / (unsigned)c.B;
+        i = r - s * (unsigned)c.B;
+        if (io.active_mask && !io.active_mask[s / (unsigned)c.A]) live = false;
+    }
+    if (live) {
+        // beam direction: closed form of the reference's running sum theta_index += increment with wrap
+        // (laser_models.py:174-184).  The running sum differs from the closed form by < 1.3e-10 after
+        // 1080 adds; only when the value sits within 1e-9 of an integer can int() disagree, and then the
+        // sum is replayed exactly.
+        const double t0 = sc.theta0[s];
+        const double td = (double)c.theta_dis;
+        double t = t0 + (double)i * c.theta_inc;
+        if (t >= td) t -= td;
+        if (fabs(t - rint(t)) < 1e-9) {
+            t = t0;
+            for (unsigned k = 0; k < i; ++k) {
+                t += c.theta_inc;
+                while (t >= td) t -= td;
+            }
+        }
+        int ti = (int)t;
+        ti = ti < c.theta_dis ? ti : c.theta_dis - 1;   // memory safety only
+        const double sn = __ldg(c.sines + ti);
+        const double cs = __ldg(c.cosines + ti);
+
+        // trace_ray, laser_models.py:129-144
+        double x = sc.scan_x[s], y = sc.scan_y[s];
+        double d = dt_lookup(m, x, y);
+        double total_d = d;
+        if (COUNT) nlook = 1;
+        while (d > c.eps && total_d <= c.max_range) {
+            x += d * cs;
+            y += d * sn;
+            d = dt_lookup(m, x, y);
+            total_d += d;
+            if (COUNT) ++nlook;
+        }
+        if (total_d > c.max_range) total_d = c.max_range;
+
+        // scan += noise, laser_models.py:450-452
+        double range = total_d;
+        if (io.noise) {
+            range += io.noise[r];
+        } else if (c.noise_std > 0.0) {
+            const uint4 bits = philox4x32_10(make_uint4(i, st.step_count[s / (unsigned)c.A], s, 0x46313130u),
+                                             make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+            range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
+        }
+        sc.scan[r] = range;
+
+        // check_ttc_jit, laser_models.py:205-213 (any-reduction; the reference's early break is irrelevant)
+        const double vel = st.x[3][s];
+        if (vel != 0.0) {
+            const double proj_vel = vel * __ldg(c.beam_cos + i);
+            const double ttc = (range - __ldg(c.side_dist + i)) / proj_vel;
+            if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
+        }
+    }
+    if (COUNT) {
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, nlook);
+        const unsigned wrays = __popc(__ballot_sync(0xffffffffu, live));
+        if ((threadIdx.x & 31) == 0 && wrays) {
+            atomicAdd(sc.lookups, (unsigned long long)wsum);
+            atomicAdd(sc.lookups + 1, (unsigned long long)wrays);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K3: post
+
+// get_trmtx + get_vertices, collision_models.py:218-260; order rl, rr, fr, fl
+__device__ __forceinline__ void get_vertices(double px, double py, double yaw, double length, double width, double* v) {
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+    const double hx[4] = { -length / 2, -length / 2, length / 2, length / 2 };
+    const double hy[4] = { width / 2, -width / 2, -width / 2, width / 2 };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = cs * hx[k] + (-sn) * hy[k] + px;
+        v[2 * k + 1] = sn * hx[k] + cs * hy[k] + py;
+    }
+}
+
+__device__ __forceinline__ int furthest_point(const double* v, double dx, double dy) {  // np.argmax: first maximum
+    int best = 0;
+    double bv = v[0] * dx + v[1] * dy;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const double d = v[2 * k] * dx + v[2 * k + 1] * dy;
+        if (d > bv) { bv = d; best = k; }
+    }
+    return best;
+}
+
+__device__ __forceinline__ void gjk_support(const double* v1, const double* v2, double dx, double dy, double& ox, double& oy) {
+    const int i = furthest_point(v1, dx, dy);
+    const int j = furthest_point(v2, -dx, -dy);
+    ox = v1[2 * i] - v2[2 * j];
+    oy = v1[2 * i + 1] - v2[2 * j + 1];
+}
+
+// tripleProduct(a, b, c) = b*(a.c) - a*(b.c), collision_models.py:52-64
+__device__ __forceinline__ void triple_product(double ax, double ay, double bx, double by, double cx, double cy,
+                                               double& ox, double& oy) {
+    const double ac = ax * cx + ay * cy;
+    const double bc = bx * cx + by * cy;
+    ox = bx * ac - ax * bc;
+    oy = by * ac - ay * bc;
+}
+
+// collision (GJK), collision_models.py:113-182
+__device__ bool gjk_collision(const double* v1, const double* v2) {
+    double s0x, s0y, s1x = 0., s1y = 0.;   // simplex rows 0 and 1 (row 2 is always the newest point a)
+    double dx = (v1[0] + v1[2] + v1[4] + v1[6]) / 4 - (v2[0] + v2[2] + v2[4] + v2[6]) / 4;
+    double dy = (v1[1] + v1[3] + v1[5] + v1[7]) / 4 - (v2[1] + v2[3] + v2[5] + v2[7]) / 4;
+    if (dx == 0 && dy == 0) dx = 1.0;
+    double ax, ay;
+    gjk_support(v1, v2, dx, dy, ax, ay);
+    s0x = ax; s0y = ay;
+    if (dx * ax + dy * ay <= 0) return false;
+    dx = -ax; dy = -ay;
+    int index = 0;
+    for (int iter = 0; iter < 1000;) {
+        gjk_support(v1, v2, dx, dy, ax, ay);
+        index += 1;
+        if (dx * ax + dy * ay <= 0) return false;
+        const double aox = -ax, aoy = -ay;
+        if (index < 2) {
+            s1x = ax; s1y = ay;
+            const double abx = s0x - ax, aby = s0y - ay;
+            triple_product(abx, aby, aox, aoy, abx, aby, dx, dy);
+            if (sqrt(dx * dx + dy * dy) < 1e-10) { dx = aby; dy = -1 * abx; }
+            continue;   // the reference does not count this pass (:154-160)
+        }
+        const double abx = s1x - ax, aby = s1y - ay;
+        const double acx = s0x - ax, acy = s0y - ay;
+        double px, py;
+        triple_product(abx, aby, acx, acy, acx, acy, px, py);      // acperp
+        if (px * aox + py * aoy >= 0) {
+            dx = px; dy = py;
+        } else {
+            triple_product(acx, acy, abx, aby, abx, aby, px, py);  // abperp
+            if (px * aox + py * aoy < 0) return true;
+            s0x = s1x; s0y = s1y;
+            dx = px; dy = py;
+        }
+        s1x = ax; s1y = ay;   // simplex[1] = simplex[2]
+        index -= 1;
+        ++iter;
+    }
+    return false;
+}
+
+// index of the first minimum of |scan_angles[k] - a| over a strictly increasing table (np.argmin semantics)
+__device__ __forceinline__ int nearest_beam(const double* __restrict__ ang, int B, double a) {
+    if (a != a) return 0;
+    int lo = 0, hi = B;   // lower_bound: first k with ang[k] >= a
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ang + mid) < a) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0;
+    if (lo == B) return B - 1;
+    const double dl = fabs(__ldg(ang + lo - 1) - a);
+    const double dr = fabs(__ldg(ang + lo) - a);
+    return (dl <= dr) ? lo - 1 : lo;
+}
+
+// get_range (+ are_collinear), laser_models.py:230-280; v3 = (cos, sin)(beam_theta + pi/2) hoisted by the caller
+__device__ __forceinline__ double get_range(double ox, double oy, double v3x, double v3y,
+                                            double vax, double vay, double vbx, double vby) {
+    const double v1x = ox - vax, v1y = oy - vay;
+    const double v2x = vbx - vax, v2y = vby - vay;
+    const double denom = v2x * v3x + v2y * v3y;
+    double distance = INFINITY;
+    if (fabs(denom) > 0.0) {
+        const double d1 = (v2x * v1y - v2y * v1x) / denom;
+        const double d2 = (v1x * v3x + v1y * v3y) / denom;
+        if (d1 >= 0.0 && d2 >= 0.0 && d2 <= 1.0) distance = d1;
+    } else {
+        const double bax = vax - ox, bay = vay - oy;
+        const double cax = ox - vbx, cay = oy - vby;
+        if (fabs(bax * cay - bay * cax) < 1e-8) {
+            const double da = sqrt((vax - ox) * (vax - ox) + (vay - oy) * (vay - oy));
+            const double db = sqrt((vbx - ox) * (vbx - ox) + (vby - oy) * (vby - oy));
+            distance = da < db ? da : db;
+        }
+    }
+    return distance;
+}
+
+constexpr int POST_THREADS = 256;
+
+__global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    const int env = blockIdx.x;
+    if (io.active_mask && !io.active_mask[env]) return;
+    const int A = c.A, B = c.B;
+    const int tid = threadIdx.x;
+    const int s_base = env * A;
+
+    __shared__ double s_pose[F110_MAX_AGENTS][3];        // own pose AFTER iTTC zeroing (ray-cast origin, :225)
+    __shared__ double s_pre[F110_MAX_AGENTS][3];         // Simulator.agent_poses: BEFORE iTTC zeroing (:587)
+    __shared__ double s_verts[F110_MAX_AGENTS * F110_MAX_AGENTS][8];  // opponent b seen by a, a's length/width
+    __shared__ int s_lo[F110_MAX_AGENTS * F110_MAX_AGENTS];
+    __shared__ int s_hi[F110_MAX_AGENTS * F110_MAX_AGENTS];
+    __shared__ int s_coll[F110_MAX_AGENTS];              // GJK flags
+    __shared__ int s_hit[F110_MAX_AGENTS];               // iTTC flags
+    __shared__ int s_lapdone[F110_MAX_AGENTS];
+
+    // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252
+    if (tid < A) {
+        const int s = s_base + tid;
+        const int hit = sc.ttc_hit[s];
+        const double px = st.x[0][s], py = st.x[1][s];
+        const double yaw_pre = sc.pre_yaw[s];
+        if (hit) { st.x[3][s] = 0.; st.x[4][s] = 0.; st.x[5][s] = 0.; st.x[6][s] = 0.; }
+        s_pose[tid][0] = px; s_pose[tid][1] = py; s_pose[tid][2] = hit ? 0. : yaw_pre;
+        s_pre[tid][0] = px; s_pre[tid][1] = py; s_pre[tid][2] = yaw_pre;
+        s_hit[tid] = hit;
+        s_coll[tid] = 0;
+    }
+    __syncthreads();
+
+    // ---- stage B: all-pairs GJK (check_collision :549-563) and per-(a, b) ray-cast windows (:206-227)
+    if (A > 1) {
+        for (int t = tid; t < A * A; t += POST_THREADS) {
+            const int a = t / A, b = t - a * A;
+            if (a == b) continue;
+            if (a < b) {
+                double va[8], vb[8];
+                const double L = __ldg(c.sim_params + P_LENGTH), Wd = __ldg(c.sim_params + P_WIDTH);
+                get_vertices(s_pre[a][0], s_pre[a][1], s_pre[a][2], L, Wd, va);
+                get_vertices(s_pre[b][0], s_pre[b][1], s_pre[b][2], L, Wd, vb);
+                if (gjk_collision(va, vb)) { s_coll[a] = 1; s_coll[b] = 1; }
+            }
+            // opponent b as seen from a: a's own length/width (ray_cast_agents :223)
+            double* v = s_verts[t];
+            get_vertices(s_pre[b][0], s_pre[b][1], s_pre[b][2], __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH),
+                         __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH), v);
+            // get_blocked_view_indices, laser_models.py:282-315
+            double sn, cs;
+            sincos(s_pose[a][2], &sn, &cs);
+            const double ego_ang = atan2(sn, cs);
+            int lo = 0, hi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double vx = v[2 * k] - s_pose[a][0], vy = v[2 * k + 1] - s_pose[a][1];
+                const double nrm = sqrt(vx * vx + vy * vy);
+                double ang = ego_ang - atan2(vy / nrm, vx / nrm);
+                if (ang > F110_PI) ang = ang - 2 * F110_PI;
+                else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
+                const int ind = nearest_beam(c.scan_angles, B, -ang);
+                if (k == 0) { lo = hi = ind; }
+                else { lo = ind < lo ? ind : lo; hi = ind > hi ? ind : hi; }
+            }
+            s_lo[t] = lo; s_hi[t] = hi;
+        }
+        __syncthreads();
+    }
+
+    // ---- stage C: finish zone / laps per agent, _check_done f110_env.py:320-348
+    const double new_time = st.time[env] + c.timestep;   // :406 (read by every thread before thread 0 writes it back)
+    if (tid < A) {
+        const int s = s_base + tid;
+        const int col = (s_coll[tid] | s_hit[tid]) ? 1 : 0;
+        const double dxp = s_pose[tid][0] - st.start_x[s];
+        const double dyp = s_pose[tid][1] - st.start_y[s];
+        const double rc = st.rot_c[env], rs = st.rot_s[env];
+        // start_rot = [[cos(-t), -sin(-t)], [sin(-t), cos(-t)]]
+        const double lx = rc * dxp + (-rs) * dyp;
+        double ty = rs * dxp + rc * dyp;
+        if (ty > 2) ty -= 2;
+        else if (ty < -2) ty = -2 - ty;
+        else ty = 0;
+        const double dist2 = lx * lx + ty * ty;
+        const bool closes = dist2 <= 0.1;
+        int near = st.near_start[s];
+        int tog = st.toggles[s];
+        if (closes && !near) { near = 1; tog += 1; }
+        else if (!closes && near) { near = 0; tog += 1; }
+        st.near_start[s] = (uint8_t)near;
+        st.toggles[s] = tog;
+        const double lapc = (double)(tog / 2);
+        st.lap_counts[s] = lapc;
+        double lapt = st.lap_times[s];
+        if (tog < 4) { lapt = new_time; st.lap_times[s] = lapt; }
+        st.collisions[s] = (uint8_t)col;
+        s_lapdone[tid] = tog >= 4;
+        s_coll[tid] = col;
+        if (io.collisions) io.collisions[s] = (uint8_t)col;
+        if (io.toggles) io.toggles[s] = tog;
+        if (io.lap_times) io.lap_times[s] = lapt;
+        if (io.lap_counts) io.lap_counts[s] = lapc;
+        if (io.state) {
+            double* o = io.state + (size_t)s * 7;
+            o[0] = s_pose[tid][0]; o[1] = s_pose[tid][1]; o[2] = st.x[2][s];
+            if (s_hit[tid]) { o[3] = 0.; o[4] = 0.; o[5] = 0.; o[6] = 0.; }
+            else { o[3] = st.x[3][s]; o[4] = s_pose[tid][2]; o[5] = st.x[5][s]; o[6] = st.x[6][s]; }
+        }
+    }
+
+    // ---- stage D: opponent ray-cast + scan outputs + lidar part of the flat observation
+    const float lm = c.lidar_max;
+    for (int idx = tid; idx < A * B; idx += POST_THREADS) {
+        const int a = idx / B;
+        const int i = idx - a * B;
+        const size_t g = (size_t)s_base * B + idx;
+        double range = sc.scan[g];
+        if (A > 1) {
+            bool have_dir = false;
+            double v3x = 0., v3y = 0.;
+            for (int b = 0; b < A; ++b) {
+                if (b == a) continue;
+                const int t = a * A + b;
+                if (i < s_lo[t] || i > s_hi[t]) continue;
+                if (!have_dir) {
+                    const double beam_theta = s_pose[a][2] + __ldg(c.scan_angles + i);
+                    sincos(beam_theta + F110_PI / 2., &v3y, &v3x);
+                    have_dir = true;
+                }
+                const double* v = s_verts[t];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int j2 = (j + 1) & 3;
+                    const double rr = get_range(s_pose[a][0], s_pose[a][1], v3x, v3y, v[2 * j], v[2 * j + 1], v[2 * j2], v[2 * j2 + 1]);
+                    if (rr < range) range = rr;
+                }
+            }
+        }
+        if (io.scans_f64) io.scans_f64[g] = range;
+        if (io.scans_f32) io.scans_f32[g] = (float)range;
+        if (a == 0 && io.obs) {   // _pack_flat_obs f110_env.py:557-560 (e = 0 hard-coded)
+            float rf = (float)range;
+            if (rf != rf) rf = lm;
+            else if (isinf(rf)) rf = rf > 0 ? lm : 0.0f;
+            rf = rf < 0.0f ? 0.0f : rf;
+            rf = rf > lm ? lm : rf;
+            io.obs[(size_t)env * (B + 8) + i] = rf / lm;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage E: done, reward, time, pose part of the observation, episode statistics
+    if (tid == 0) {
+        bool all_laps = true;
+        for (int a = 0; a < A; ++a) all_laps = all_laps && s_lapdone[a];
+        const bool done = (s_coll[c.ego] != 0) || all_laps;   // f110_env.py:350
+        st.time[env] = new_time;
+        if (io.time) io.time[env] = new_time;
+        if (io.reward) io.reward[env] = (float)c.timestep;
+        if (io.terminated) io.terminated[env] = done ? 1 : 0;
+        if (io.obs) {   // f110_env.py:563-579: slots for agents 0 and 1 (zeros when A == 1)
+            float* q = io.obs + (size_t)env * (B + 8) + B;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k < A) {
+                    q[4 * k] = (float)s_pose[k][0];
+                    q[4 * k + 1] = (float)s_pose[k][1];
+                    q[4 * k + 2] = (float)wrap_angle(s_pose[k][2]);
+                    q[4 * k + 3] = s_coll[k] ? 1.0f : 0.0f;
+                } else {
+                    q[4 * k] = q[4 * k + 1] = q[4 * k + 2] = q[4 * k + 3] = 0.0f;
+                }
+            }
+        }
+        if (done) {
+            atomicAdd(sc.stats + F110_STAT_EPISODES, 1.0);
+            atomicAdd(sc.stats + F110_STAT_EPISODE_STEPS, (double)st.step_count[env] + 1.0);
+            atomicAdd(sc.stats + F110_STAT_EPISODE_TIME, new_time);
+            if (s_coll[c.ego]) atomicAdd(sc.stats + F110_STAT_EGO_COLLISIONS, 1.0);
+            if (all_laps) atomicAdd(sc.stats + F110_STAT_LAPS_DONE, 1.0);
+        }
+    }
+}
+
+}  // namespace
+
+void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
+    const int threads = 128;
+    dynamics_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, sc, io);
+}
+
+void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
+                  bool count_lookups, cudaStream_t s) {
+    const unsigned total = (unsigned)c.NA * (unsigned)c.B;
+    const unsigned threads = 256;
+    const unsigned blocks = (total + threads - 1) / threads;
+    if (count_lookups) lidar_kernel<true><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+    else lidar_kernel<false><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+}
+
+void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
+    post_kernel<<<c.N, POST_THREADS, 0, s>>>(c, st, sc, io);
+}
+
+void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {
+    const int threads = 128;
+    sim_reset_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, poses, mask);
+}

@@ -1,0 +1,99 @@
+"""Simulator: the reference's lower boundary (base_classes.py:464-643) on top of the CUDA backend.
+
+Same constructor, same methods, same return dictionary and the same exceptions; the physics, lidar,
+GJK and iTTC run in libf110_b200.so.  One instance drives N = 1 env (the reference's shape); the
+batched form is backend.BatchSim / env.F110VecEnv.
+"""
+from enum import Enum
+
+import numpy as np
+import torch
+
+from .backend import ALL_OUTPUTS, BatchSim
+
+
+class Integrator(Enum):   # base_classes.py:40-42
+    RK4 = 1
+    Euler = 2
+
+
+class Simulator(object):
+    """Drop-in for f110_gym.envs.base_classes.Simulator.
+
+    Lidar noise: ``noise='numpy'`` (default) draws ``Generator.normal(0, 0.01, num_beams)`` per agent per
+    step on the host from ``default_rng(seed)`` re-seeded on reset -- bit-identical to the reference's
+    stream (base_classes.py:119,204; laser_models.py:450-452) -- and uploads it; ``noise='device'`` uses the
+    library's Philox stream (same N(0, 0.01^2) law, different bits); ``noise=None`` disables it.
+    """
+
+    def __init__(self, params, num_agents, seed, time_step=0.01, ego_idx=0, integrator=Integrator.RK4, lidar_dist=0.0,
+                 noise='numpy', device=None, num_beams=1080, fov=4.7):
+        if not isinstance(integrator, Integrator) and integrator not in (1, 2):
+            raise SyntaxError("Invalid Integrator Specified. Provided %s. Please choose RK4 or Euler" % (integrator,))
+        self.num_agents = num_agents
+        self.seed = seed
+        self.time_step = time_step
+        self.ego_idx = ego_idx
+        self.params = params
+        self.num_beams = num_beams
+        self.noise_mode = noise
+        self.agent_poses = np.empty((self.num_agents, 3))
+        self.collisions = np.zeros((self.num_agents,))
+        self.collision_idx = -1 * np.ones((self.num_agents,))
+        self.backend = BatchSim(1, num_agents, params=params, seed=seed, timestep=time_step, integrator=integrator,
+                                ego_idx=ego_idx, lidar_dist=lidar_dist, num_beams=num_beams, fov=fov,
+                                noise_std=0.01 if noise == 'device' else 0.0, device=device, outputs=ALL_OUTPUTS)
+        # every RaceCar owns default_rng(seed) (all agents share the seed => identical streams)
+        self._rngs = None
+        self._pending_reset = None
+        self.last = None
+
+    def set_map(self, map_path, map_ext):
+        self.backend.set_map(map_path, map_ext)
+
+    def update_params(self, params, agent_idx=-1):
+        if agent_idx >= self.num_agents:
+            raise IndexError('Index given is out of bounds for list of agents.')
+        self.backend.update_params(params, agent_idx)
+
+    def reset(self, poses):
+        poses = np.asarray(poses, dtype=np.float64)
+        if poses.shape[0] != self.num_agents:
+            raise ValueError('Number of poses for reset does not match number of agents.')
+        self.backend.sim_reset(poses[None])
+        self._rngs = [np.random.default_rng(seed=self.seed) for _ in range(self.num_agents)]
+
+    def _noise(self):
+        if self.noise_mode != 'numpy':
+            return None
+        if self._rngs is None:
+            raise AttributeError("scan_rng is only created by reset() for cars other than the first (base_classes.py:119,204)")
+        return np.stack([r.normal(0., 0.01, size=self.num_beams) for r in self._rngs])[None]
+
+    def _step_raw(self, control_inputs, reset_mask=None, reset_poses=None):
+        out = self.backend.step(control_inputs, self._noise(), reset_mask, reset_poses)
+        torch.cuda.current_stream(self.backend.device).synchronize()
+        self.last = {k: v.cpu().numpy() for k, v in out.items()}
+        return self.last
+
+    def step(self, control_inputs):
+        control_inputs = np.asarray(control_inputs)
+        if control_inputs.dtype != np.float32:
+            control_inputs = control_inputs.astype(np.float64)
+        o = self._step_raw(control_inputs.reshape(1, self.num_agents, 2))
+        return self._observations(o)
+
+    def _observations(self, o):
+        st = o['state'][0]
+        self.agent_poses = st[:, [0, 1, 4]].copy()
+        self.collisions = o['collisions'][0].astype(np.float64)
+        observations = {'ego_idx': self.ego_idx,
+                        'scans': [o['scans_f64'][0, i].copy() for i in range(self.num_agents)],
+                        'poses_x': [st[i, 0] for i in range(self.num_agents)],
+                        'poses_y': [st[i, 1] for i in range(self.num_agents)],
+                        'poses_theta': [st[i, 4] for i in range(self.num_agents)],
+                        'linear_vels_x': [st[i, 3] for i in range(self.num_agents)],
+                        'linear_vels_y': [0. for _ in range(self.num_agents)],
+                        'ang_vels_z': [st[i, 5] for i in range(self.num_agents)],
+                        'collisions': self.collisions}
+        return observations

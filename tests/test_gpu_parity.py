@@ -1,0 +1,305 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against
+  * the golden vectors recorded from the unmodified reference (tests/golden), and
+  * the CPU oracle on the same seeded inputs, at sizes the oracle finishes in seconds, and
+  * size-independent properties at the BASELINE.json batch sizes.
+
+Tolerances are BASELINE.json's north_star: collision / done / lap flags bit-exact over the rollout, fp64
+vehicle state within 1e-9 absolute, lidar within 1e-6 m on >= 99.9 % of beams (outliers counted).
+"""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-9
+SCAN_TOL = 1e-6
+SCAN_FRAC = 0.999
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+class GpuBackend(object):
+    """Adapter: BatchSim (device tensors) -> the numpy dict compare_rollout expects."""
+
+    def __init__(self, num_envs, num_agents, map_name, **kw):
+        _torch()
+        from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+        self.sim = BatchSim(num_envs, num_agents, outputs=ALL_OUTPUTS, noise_std=kw.pop('noise_std', 0.0), **kw)
+        s, c, a, bc, sd = H.tables()
+        self.sim.set_tables(s, c)
+        self.sim.set_beam_tables(a, bc, sd)
+        self.sim.set_map_arrays(*H.golden_map(map_name))
+
+    def _np(self, o):
+        import torch
+        torch.cuda.synchronize()
+        d = {k: v.cpu().numpy() for k, v in o.items()}
+        d['scans'] = d['scans_f64']
+        return d
+
+    def reset(self, poses, noise=None):
+        return self._np(self.sim.reset(poses, noise))
+
+    def step(self, actions, noise=None, **kw):
+        return self._np(self.sim.step(actions, noise, **kw))
+
+
+def make_gpu(num_agents, map_name, **kw):
+    return GpuBackend(1, num_agents, map_name, **kw)
+
+
+def make_oracle(num_envs, num_agents, map_name, **kw):
+    from oracle.f110_oracle import Oracle
+    o = Oracle(num_envs, num_agents, **kw)
+    s, c, a, bc, sd = H.tables()
+    o.set_tables(s, c)
+    o.set_beam_tables(a, bc, sd)
+    o.set_map_arrays(*H.golden_map(map_name))
+    return o
+
+
+# ----------------------------------------------------------------------------- golden rollouts
+
+@pytest.mark.parametrize("name", sorted(H.ROLLOUT_MAP))
+def test_golden_rollouts(name):
+    r = H.compare_rollout(name, make_gpu, state_tol=STATE_TOL, scan_tol=SCAN_TOL, scan_frac=SCAN_FRAC, obs_tol=1e-6)
+    print(name, r)
+
+
+@pytest.mark.parametrize("map_name", ["Shanghai_map", "straight_corridor"])
+def test_golden_scans_noise_free(map_name):
+    """ScanSimulator2D.scan(pose, None): the ray-march alone; expected bit-exact (same tables, no FMA)."""
+    g = H.load('scans')
+    poses, ref = g[map_name + '__poses'], g[map_name + '__scans']
+    be = GpuBackend(len(poses), 1, map_name)
+    be.sim.sim_reset(poses[:, None, :])
+    # a zero-velocity car does not move in one zero-action step: the scan is taken at the reset pose
+    out = be.step(None, np.zeros((len(poses), 1, 1080)))
+    d = np.abs(out['scans'][:, 0] - ref)
+    # wrap() of the yaw happens before the scan; poses outside [-pi, pi) only change theta by an exact 2*pi multiple
+    frac_exact = float((d == 0).mean())
+    print(map_name, 'max', d.max(), 'exact fraction', frac_exact)
+    assert (d <= SCAN_TOL).mean() >= SCAN_FRAC
+
+
+def test_c1_single_agent_sim_rollout():
+    g = H.load('rollout_c1_single')
+    be = make_gpu(1, 'Shanghai_map')
+    rng = None
+    worst = 0.0
+    for t in range(g['state'].shape[0]):
+        if g['resets'][t] or t == 0:
+            rng = np.random.default_rng(int(g['seed']))
+            be.sim.sim_reset(g['pose'][None, None])
+        out = be.step(g['action'][None], rng.normal(0., 0.01, size=1080)[None, None])
+        worst = max(worst, np.abs(out['state'][0, 0] - g['state'][t]).max())
+        assert out['collisions'][0, 0] == g['collisions'][t], t
+        if t % int(g['every']) == 0:
+            assert (np.abs(out['scans'][0, 0] - g['scans'][t // int(g['every'])]) <= SCAN_TOL).mean() >= SCAN_FRAC
+    assert worst <= STATE_TOL
+    print('c1 worst state diff', worst)
+
+
+# ----------------------------------------------------------------------------- oracle on seeded batches
+
+@pytest.mark.parametrize("num_envs,num_agents", [(64, 1), (48, 2), (16, 3)])
+def test_batched_vs_oracle(num_envs, num_agents):
+    """Random start poses on the Shanghai centerline, random f32 actions, injected noise, masks and resets."""
+    rng = np.random.default_rng(100 + num_envs)
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    idx = rng.integers(0, len(cl), size=num_envs)
+    poses = np.zeros((num_envs, num_agents, 3))
+    for a in range(num_agents):
+        j = (idx + 18 * a) % len(cl)
+        poses[:, a] = cl[j]
+        poses[:, a, 1] += 0.25 * a
+    be = GpuBackend(num_envs, num_agents, 'Shanghai_map')
+    orc = make_oracle(num_envs, num_agents, 'Shanghai_map')
+    T = 120
+    stats = dict(state=0.0, outl=0, beams=0)
+    prev_term = np.zeros(num_envs, np.uint8)
+    for t in range(T):
+        noise = rng.normal(0, 0.01, size=(num_envs, num_agents, 1080))
+        if t == 0:
+            g = be.reset(poses, noise)
+            c = orc.reset(poses, noise)
+        else:
+            act = rng.uniform([-0.4189, 0], [0.4189, 12], size=(num_envs, num_agents, 2)).astype(np.float32)
+            kw = {}
+            if t % 7 == 0:       # auto-reset of the envs that terminated + a partial active mask
+                kw = dict(reset_mask=prev_term.copy(), reset_poses=poses)
+            if t % 11 == 0:
+                kw['active_mask'] = (rng.uniform(size=num_envs) < 0.7).astype(np.uint8)
+            g = be.step(act, noise, **kw)
+            c = orc.step(act, noise, **kw)
+        for k in ('collisions', 'terminated', 'toggles', 'lap_counts'):
+            assert np.array_equal(g[k], c[k]), (k, t)
+        assert np.allclose(g['lap_times'], c['lap_times'], rtol=0, atol=1e-12)
+        assert np.allclose(g['time'], c['time'], rtol=0, atol=1e-12)
+        d = np.abs(g['state'] - c['state']).max()
+        stats['state'] = max(stats['state'], d)
+        assert d <= STATE_TOL, (t, d)
+        ds = np.abs(g['scans'] - c['scans'])
+        stats['outl'] += int((ds > SCAN_TOL).sum()); stats['beams'] += ds.size
+        assert np.abs(g['obs'] - c['obs']).max() <= 1e-6 or (ds > SCAN_TOL).any()
+        prev_term = c['terminated'].copy()
+    print('batched vs oracle', num_envs, num_agents, stats)
+    assert stats['outl'] <= (1 - SCAN_FRAC) * stats['beams']
+
+
+def test_known_answer_dynamics_on_device():
+    """The reference's stiff high-speed test state (dynamic_models.py:262-266, CommonRoad vehicle-2 params
+    :232-253) through ONE Euler step of the device kernel: x1 == x0 + dt * f(x0, u) with f from the oracle,
+    whose RHS is pinned to f_st_gt (:258) by tests/test_oracle_golden.py."""
+    torch = _torch()
+    from oracle.f110_oracle import Oracle
+    from tests.test_oracle_golden import TEST_PARAMS
+    x_st = np.array([2.0233348142065677, 0.0041907137716636, 0.0197545248559617, 15.7216236334290116,
+                     0.0025857914776859, 0.0529001056654038, 0.0033012170610298])
+    p = dict(TEST_PARAMS)
+    p['lidar_max'] = 30.0
+    dt = 1e-3
+    be = GpuBackend(1, 1, 'open_square', params=p, integrator=2, timestep=dt)
+    # inject the state through the checkpoint blob: x[k] are the first seven 256-byte-aligned arrays (NA = 1)
+    blob = be.sim.state_dict()['blob'].clone()
+    blob.view(torch.float64)[0:7 * 32:32] = torch.tensor(x_st, dtype=torch.float64, device=blob.device)
+    be.sim.load_state_dict({'blob': blob, 'N': 1, 'A': 1, 'B': 1080})
+    out = be.step(np.array([[[0.5, 30.0]]], np.float64), np.zeros((1, 1, 1080)))
+    # pid(): the steering FIFO is still empty -> steer = 0 -> sv = -sv_max; speed error -> accl clipped to +a_max
+    f = Oracle(1, 1).vehicle_dynamics_st(x_st, np.array([-p['sv_max'], p['a_max']]), p)
+    x1 = x_st + dt * f
+    assert np.abs(out['state'][0, 0] - x1).max() < 1e-13
+
+
+def test_gjk_known_answer_on_device():
+    """collision_models.py:313-324 geometry as cars: overlapping / separated poses -> collision flags."""
+    be = GpuBackend(1, 4, 'open_square')
+    poses = np.array([[[0.0, 0.0, 0.0], [0.3, 0.1, 0.4], [3.0, 3.0, 1.0], [-4.0, 2.0, 0.0]]])
+    out = be.reset(poses, np.zeros((1, 4, 1080)))
+    assert out['collisions'][0].tolist() == [1, 1, 0, 0]
+    assert bool(out['terminated'][0])
+    from oracle.f110_oracle import Oracle
+    orc = make_oracle(1, 4, 'open_square')
+    c = orc.reset(poses, np.zeros((1, 4, 1080)))
+    assert np.array_equal(c['collisions'], out['collisions'])
+    assert (np.abs(c['scans'] - out['scans']) <= SCAN_TOL).all()
+
+
+# ----------------------------------------------------------------------------- properties at full size
+
+def test_full_size_properties():
+    """BASELINE config 3 shape (4096 envs x 1 agent x 1080 beams): replicated envs must produce replicated
+    results (no cross-env leakage), scans bounded by max_range + noise, state finite, and a checkpoint
+    round-trip must reproduce the same next step bit for bit."""
+    torch = _torch()
+    N = 4096
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    idx = np.linspace(0, len(cl) - 1, N // 4).round().astype(int)
+    poses = np.repeat(cl[idx][:, None, :], 4, axis=0)              # every start pose 4x
+    be = GpuBackend(N, 1, 'Shanghai_map')
+    rng = np.random.default_rng(5)
+    be.sim.reset(poses, None)
+    for t in range(30):
+        act = np.repeat(rng.uniform([-0.4189, 0], [0.4189, 10], size=(N // 4, 1, 2)).astype(np.float32), 4, axis=0)
+        out = be.sim.step(act, None)
+    torch.cuda.synchronize()
+    st = out['state'].cpu().numpy().reshape(N // 4, 4, 7)
+    sc = out['scans_f64'].cpu().numpy().reshape(N // 4, 4, 1080)
+    assert np.isfinite(st).all()
+    assert (st == st[:, :1]).all() and (sc == sc[:, :1]).all()
+    assert sc.max() <= 30.0 and sc.min() >= 0.0
+    obs = out['obs'].cpu().numpy()
+    assert obs[:, :1080].min() >= 0.0 and obs[:, :1080].max() <= 1.0
+    # checkpoint round trip
+    sd = be.sim.state_dict()
+    act = rng.uniform([-0.4189, 0], [0.4189, 10], size=(N, 1, 2)).astype(np.float32)
+    a1 = {k: v.clone() for k, v in be.sim.step(act, None).items()}
+    be.sim.load_state_dict(sd)
+    a2 = be.sim.step(act, None)
+    torch.cuda.synchronize()
+    for k in a1:
+        assert torch.equal(a1[k], a2[k]), k
+
+
+def test_device_noise_statistics():
+    """Throughput mode: on-device Philox + Box-Muller noise ~ N(0, 0.01^2), independent across envs."""
+    torch = _torch()
+    N = 512
+    be = GpuBackend(N, 1, 'open_square', noise_std=0.01, seed=7)
+    poses = np.zeros((N, 1, 3))
+    a = {k: v.clone() for k, v in be.sim.reset(poses, None).items()}
+    clean = GpuBackend(1, 1, 'open_square')
+    c = clean.reset(poses[:1], np.zeros((1, 1, 1080)))
+    torch.cuda.synchronize()
+    nz = a['scans_f64'].cpu().numpy()[:, 0] - c['scans'][0, 0][None]
+    assert abs(nz.mean()) < 2e-4 and abs(nz.std() - 0.01) < 2e-4
+    assert abs(np.corrcoef(nz[0], nz[1])[0, 1]) < 0.15
+    k = ((nz / 0.01) ** 4).mean()
+    assert 2.8 < k < 3.2
+
+
+def test_env_api_matches_reference_surface(tmp_path):
+    """F110Env drop-in: kwargs, return types, info keys/dtypes (f110_env.py:586-602) and the golden rollout."""
+    _torch()
+    import f110_gymnasium_ros2_jazzy_b200 as f
+    map_dir, name = H.write_map_files('Shanghai_map', str(tmp_path))
+    env = f.make('f110_gym:f110-v0', map_dir=map_dir, map=name, map_ext='.png', num_agents=2)
+    s, c, a, bc, sd = H.tables()
+    env.sim.backend.set_tables(s, c)
+    g = H.load('rollout_const_shanghai')
+    obs, info = env.reset(options=g['poses'])
+    assert obs.dtype == np.float32 and obs.shape == (1088,)
+    assert info['time'] == pytest.approx(0.01)
+    assert np.abs(obs - g['obs'][0]).max() <= 1e-6
+    for k, dt_ in [('poses_x', np.float32), ('poses_y', np.float32), ('poses_theta', np.float32),
+                   ('linear_vels_x', np.float32), ('linear_vels_y', np.float32), ('ang_vels_z', np.float32),
+                   ('collisions', np.int8), ('lap_times', np.float32), ('lap_counts', np.float32)]:
+        assert info[k].dtype == dt_ and info[k].shape == (2,), k
+    assert len(info['scans']) == 2 and info['scans'][1].dtype == np.float32 and info['scans'][1].shape == (1080,)
+    first_term = None
+    for t in range(g['actions'].shape[0]):
+        obs, r, term, trunc, info = env.step(g['actions'][t])
+        assert r == 0.01 and trunc is False and isinstance(term, bool)
+        assert term == bool(g['terminated'][t + 1]), t
+        assert np.array_equal(info['collisions'], g['collisions'][t + 1].astype(np.int8))
+        if term and first_term is None:
+            first_term = t
+    assert first_term == 220     # ego terminates (TTC) at the 221st step
+    with pytest.raises(ValueError):
+        env.reset(options=np.zeros((3, 3)))
+    with pytest.raises(IndexError):
+        env.update_params(env.params, index=5)
+    env.close()
+
+
+def test_map_not_set_raises():
+    _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import BatchSim
+    sim = BatchSim(2, 1)
+    with pytest.raises(ValueError, match="Map is not set"):
+        sim.step(None)
+
+
+def test_step_host_matches_device_path():
+    torch = _torch()
+    N = 32
+    be = GpuBackend(N, 2, 'open_square')
+    b2 = GpuBackend(N, 2, 'open_square')
+    rng = np.random.default_rng(3)
+    poses = np.zeros((N, 2, 3)); poses[:, 1, 0] = 2.0; poses[:, :, 1] = rng.uniform(-3, 3, size=(N, 1))
+    noise = rng.normal(0, 0.01, size=(N, 2, 1080))
+    d = be.reset(poses, noise)
+    h = b2.sim.step_host(None, noise, np.ones(N, np.uint8), poses)
+    for t in range(5):
+        act = rng.uniform([-0.4, 0], [0.4, 8], size=(N, 2, 2)).astype(np.float32)
+        d = be.step(act, noise)
+        h = b2.sim.step_host(act, noise)
+    for k in ('obs', 'state', 'scans_f64', 'terminated', 'collisions'):
+        assert np.array_equal(d[k], h[k].numpy()), k
