@@ -302,7 +302,9 @@ def main():
         # ---- CPU arm beside it
         cpu = None
         if not args.no_cpu_baseline:
-            c = cpu_arm(args, args.cpu_steps or 40, 3)
+            probe = cpu_arm(args, 5, 2)
+            steps = args.cpu_steps or int(min(400, max(20, 2.0 / (probe['seconds'] / 5))))   # ~2 s wall on all threads
+            c = cpu_arm(args, steps, 3)
             cpu = {"value": c['value'], "unit": "env-steps/s", "cores": c['threads'], "kind": "port",
                    "sample": "%d envs x %d steps of the same workload, oracle/f110_oracle.c on %d threads (%.1f s)"
                              % (c['envs'], c['steps'], c['threads'], c['seconds'])}

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -66,6 +67,7 @@ struct F110Sim {
     char* io_blob = nullptr; size_t io_bytes = 0;
     int64_t launches = 0;
     bool timing = false;
+    int lidar_threads = 128;
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
 };
 
@@ -117,7 +119,7 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
     }
     launch_dynamics(sim->c, sim->st, sim->sc, io, s);
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[1], s));
-    launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, s);
+    launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_threads, s);
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
     launch_post(sim->c, sim->st, sim->sc, io, s);
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
@@ -157,6 +159,10 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->cfg = *cfg;
     const int N = cfg->num_envs, A = cfg->num_agents, B = cfg->num_beams, NA = N * A;
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
+    if (const char* e = getenv("F110_LIDAR_THREADS")) {   // tuning knob, multiple of 32 in [32, 256]
+        const int t = atoi(e);
+        if (t >= 32 && t <= 256 && t % 32 == 0) sim->lidar_threads = t;
+    }
 
     Arena measure;
     layout_state(measure, sim->st, N, NA);
@@ -227,7 +233,8 @@ void f110_destroy(F110Sim* sim) {
 int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
                  double orig_x, double orig_y, double orig_cos, double orig_sin) {
     if (!sim || !dt || height < 1 || width < 1 || !(resolution > 0)) return fail(F110_ERR_INVALID, "bad map arguments");
-    if ((double)height * width >= 2147483648.0) return fail(F110_ERR_INVALID, "map too large for 32-bit cell indices");
+    if ((double)height * width >= 2147483648.0 || height > (1 << 24) || width > (1 << 24))
+        return fail(F110_ERR_INVALID, "map too large (need H*W < 2^31 and H, W <= 2^24)");
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
     double* d = nullptr;
@@ -239,7 +246,8 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
     sim->d_map = d;
     MapView& m = sim->map;
     m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; m.inv_res = 1.0 / resolution;
+    m.res = resolution; m.inv20 = (1.0 / resolution) * 1048576.0;
+    m.w20 = (unsigned long long)width << 20; m.h20 = (unsigned long long)height << 20;
     m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
     m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
     sim->map_set = true;

@@ -271,19 +271,50 @@ __global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restri
 
 // ---------------------------------------------------------------- K2: lidar
 
-// xy_2_rc + distance_transform, laser_models.py:55-104
+// xy_2_rc + distance_transform, laser_models.py:55-104 -- the exact restatement (two IEEE divisions).
+// Kept out of line: the hot loop only comes here for the ~1e-5 of lookups that fall in the guard band.
+__device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double res, double wres, double hres, int W, int last) {
+    int idx;
+    if (x_rot < 0 || x_rot >= wres || y_rot < 0 || y_rot >= hres) {
+        idx = last;   // (r, c) = (-1, -1): numba wraps the negative indices to dt[H-1][W-1]
+    } else {
+        const int col = (int)(x_rot / res);
+        const int row = (int)(y_rot / res);
+        idx = row * W + col;
+        idx = idx < 0 ? 0 : (idx > last ? last : idx);   // memory safety for NaN poses / the 1-ulp wres edge
+    }
+    return idx;
+}
+
+// Cell index without the two fp64 divisions.  q20 = x_rot * (2^20 / res) is the quotient in 2^-20 cell units;
+// fl(x*inv)*2^20 == fl(x*(inv*2^20)) because scaling by a power of two commutes with rounding.  Its error
+// against the true quotient is < 2.3e-16 relative (< 0.004 units for maps up to 2^24 cells), and the
+// reference's own rounded quotient is within half an ulp of the true one, so whenever the 20 fractional bits
+// are at least GUARD units away from both cell edges, trunc(q) is exactly the reference's int(x_rot/res) and
+// (0 <= q < W) is exactly its in-map test.  Everything else (cell edges, map border, negative, NaN, huge)
+// takes the exact path.
+template <bool IDENT>
 __device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y) {
     const double x_trans = x - m.ox;
     const double y_trans = y - m.oy;
-    const double x_rot = x_trans * m.oc + y_trans * m.os;
-    const double y_rot = -x_trans * m.os + y_trans * m.oc;
-    int idx;
-    if (x_rot < 0 || x_rot >= m.wres || y_rot < 0 || y_rot >= m.hres) {
-        idx = m.last;   // (r, c) = (-1, -1) wraps to dt[H-1][W-1]
+    double x_rot, y_rot;
+    if (IDENT) {          // orig_c == 1, orig_s == 0: x*1 + y*0 == x and -x*0 + y*1 == y exactly
+        x_rot = x_trans; y_rot = y_trans;
     } else {
-        const int col = (int)(x_rot / m.res);
-        const int row = (int)(y_rot / m.res);
-        idx = row * m.W + col;
+        x_rot = x_trans * m.oc + y_trans * m.os;
+        y_rot = -x_trans * m.os + y_trans * m.oc;
+    }
+    const long long ix = __double2ll_rz(x_rot * m.inv20);
+    const long long iy = __double2ll_rz(y_rot * m.inv20);
+    constexpr unsigned GUARD = 2u, FRAC = 0xFFFFFu;
+    const unsigned fx = ((unsigned)ix & FRAC) - GUARD;
+    const unsigned fy = ((unsigned)iy & FRAC) - GUARD;
+    int idx;
+    if (fx <= FRAC - 2u * GUARD && fy <= FRAC - 2u * GUARD &&
+        (unsigned long long)ix < m.w20 && (unsigned long long)iy < m.h20) {
+        idx = (int)(iy >> 20) * m.W + (int)(ix >> 20);
+    } else {
+        idx = cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last);
     }
     return __ldg(m.dt + idx);
 }
@@ -306,7 +337,19 @@ __device__ __forceinline__ float gaussian_from_bits(uint32_t a, uint32_t b) {
     return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
 }
 
-template <bool COUNT>
+// _pack_flat_obs lidar channel, f110_env.py:557-560
+__device__ __forceinline__ float obs_lidar(double range, float lm) {
+    float rf = (float)range;
+    if (rf != rf) rf = lm;
+    else if (isinf(rf)) rf = rf > 0 ? lm : 0.0f;
+    rf = rf < 0.0f ? 0.0f : rf;
+    rf = rf > lm ? lm : rf;
+    return rf / lm;
+}
+
+// COUNT : count dt lookups (roofline L-bar)            IDENT : map origin yaw == 0
+// DIRECT: A == 1, no opponent ray-cast can follow, so the scan goes straight to the caller's buffers
+template <bool COUNT, bool IDENT, bool DIRECT>
 __global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
     const unsigned total = (unsigned)c.NA * (unsigned)c.B;
     const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,17 +384,18 @@ __global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimSt
 
         // trace_ray, laser_models.py:129-144
         double x = sc.scan_x[s], y = sc.scan_y[s];
-        double d = dt_lookup(m, x, y);
+        const double eps = c.eps, max_range = c.max_range;
+        double d = dt_lookup<IDENT>(m, x, y);
         double total_d = d;
         if (COUNT) nlook = 1;
-        while (d > c.eps && total_d <= c.max_range) {
+        while (d > eps && total_d <= max_range) {
             x += d * cs;
             y += d * sn;
-            d = dt_lookup(m, x, y);
+            d = dt_lookup<IDENT>(m, x, y);
             total_d += d;
             if (COUNT) ++nlook;
         }
-        if (total_d > c.max_range) total_d = c.max_range;
+        if (total_d > max_range) total_d = max_range;
 
         // scan += noise, laser_models.py:450-452
         double range = total_d;
@@ -362,7 +406,13 @@ __global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimSt
                                              make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
             range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
         }
-        sc.scan[r] = range;
+        if (DIRECT) {
+            if (io.scans_f64) io.scans_f64[r] = range;
+            if (io.scans_f32) io.scans_f32[r] = (float)range;
+            if (io.obs) io.obs[(size_t)s * (c.B + 8) + i] = obs_lidar(range, c.lidar_max);
+        } else {
+            sc.scan[r] = range;
+        }
 
         // check_ttc_jit, laser_models.py:205-213 (any-reduction; the reference's early break is irrelevant)
         const double vel = st.x[3][s];
@@ -646,12 +696,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
         if (io.scans_f64) io.scans_f64[g] = range;
         if (io.scans_f32) io.scans_f32[g] = (float)range;
         if (a == 0 && io.obs) {   // _pack_flat_obs f110_env.py:557-560 (e = 0 hard-coded)
-            float rf = (float)range;
-            if (rf != rf) rf = lm;
-            else if (isinf(rf)) rf = rf > 0 ? lm : 0.0f;
-            rf = rf < 0.0f ? 0.0f : rf;
-            rf = rf > lm ? lm : rf;
-            io.obs[(size_t)env * (B + 8) + i] = rf / lm;
+            io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
         }
     }
     __syncthreads();
@@ -689,6 +734,66 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     }
 }
 
+// K3 for A == 1: nothing to ray-cast and no pair to test, the lidar kernel already wrote the scans -> one thread
+// per env applies the iTTC consequence and the finish-zone / done bookkeeping (same statements as post_kernel).
+__global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= c.N) return;
+    if (io.active_mask && !io.active_mask[env]) return;
+    const int s = env;
+    const int hit = sc.ttc_hit[s];
+    const double px = st.x[0][s], py = st.x[1][s];
+    double yaw = sc.pre_yaw[s];
+    if (hit) { st.x[3][s] = 0.; st.x[4][s] = 0.; st.x[5][s] = 0.; st.x[6][s] = 0.; yaw = 0.; }
+    const double new_time = st.time[env] + c.timestep;
+    const double dxp = px - st.start_x[s];
+    const double dyp = py - st.start_y[s];
+    const double rc = st.rot_c[env], rs = st.rot_s[env];
+    const double lx = rc * dxp + (-rs) * dyp;
+    double ty = rs * dxp + rc * dyp;
+    if (ty > 2) ty -= 2;
+    else if (ty < -2) ty = -2 - ty;
+    else ty = 0;
+    const bool closes = (lx * lx + ty * ty) <= 0.1;
+    int near = st.near_start[s];
+    int tog = st.toggles[s];
+    if (closes && !near) { near = 1; tog += 1; }
+    else if (!closes && near) { near = 0; tog += 1; }
+    st.near_start[s] = (uint8_t)near;
+    st.toggles[s] = tog;
+    const double lapc = (double)(tog / 2);
+    st.lap_counts[s] = lapc;
+    double lapt = st.lap_times[s];
+    if (tog < 4) { lapt = new_time; st.lap_times[s] = lapt; }
+    st.collisions[s] = (uint8_t)hit;
+    st.time[env] = new_time;
+    const bool done = hit || tog >= 4;
+    if (io.collisions) io.collisions[s] = (uint8_t)hit;
+    if (io.toggles) io.toggles[s] = tog;
+    if (io.lap_times) io.lap_times[s] = lapt;
+    if (io.lap_counts) io.lap_counts[s] = lapc;
+    if (io.state) {
+        double* o = io.state + (size_t)s * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) o[k] = st.x[k][s];
+    }
+    if (io.time) io.time[env] = new_time;
+    if (io.reward) io.reward[env] = (float)c.timestep;
+    if (io.terminated) io.terminated[env] = done ? 1 : 0;
+    if (io.obs) {
+        float* q = io.obs + (size_t)env * (c.B + 8) + c.B;
+        q[0] = (float)px; q[1] = (float)py; q[2] = (float)wrap_angle(yaw); q[3] = hit ? 1.0f : 0.0f;
+        q[4] = q[5] = q[6] = q[7] = 0.0f;
+    }
+    if (done) {
+        atomicAdd(sc.stats + F110_STAT_EPISODES, 1.0);
+        atomicAdd(sc.stats + F110_STAT_EPISODE_STEPS, (double)st.step_count[env] + 1.0);
+        atomicAdd(sc.stats + F110_STAT_EPISODE_TIME, new_time);
+        if (hit) atomicAdd(sc.stats + F110_STAT_EGO_COLLISIONS, 1.0);
+        if (tog >= 4) atomicAdd(sc.stats + F110_STAT_LAPS_DONE, 1.0);
+    }
+}
+
 }  // namespace
 
 void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
@@ -696,17 +801,31 @@ void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& s
     dynamics_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, sc, io);
 }
 
+template <bool COUNT, bool IDENT>
+static void launch_lidar_t(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc,
+                           const F110StepIO& io, unsigned blocks, unsigned threads, cudaStream_t s) {
+    if (c.A == 1) lidar_kernel<COUNT, IDENT, true><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+    else lidar_kernel<COUNT, IDENT, false><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+}
+
 void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
-                  bool count_lookups, cudaStream_t s) {
+                  bool count_lookups, int threads_per_block, cudaStream_t s) {
     const unsigned total = (unsigned)c.NA * (unsigned)c.B;
-    const unsigned threads = 256;
+    const unsigned threads = (unsigned)threads_per_block;
     const unsigned blocks = (total + threads - 1) / threads;
-    if (count_lookups) lidar_kernel<true><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
-    else lidar_kernel<false><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+    const bool ident = (m.oc == 1.0 && m.os == 0.0);
+    if (count_lookups) {
+        if (ident) launch_lidar_t<true, true>(c, m, st, sc, io, blocks, threads, s);
+        else launch_lidar_t<true, false>(c, m, st, sc, io, blocks, threads, s);
+    } else {
+        if (ident) launch_lidar_t<false, true>(c, m, st, sc, io, blocks, threads, s);
+        else launch_lidar_t<false, false>(c, m, st, sc, io, blocks, threads, s);
+    }
 }
 
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
-    post_kernel<<<c.N, POST_THREADS, 0, s>>>(c, st, sc, io);
+    if (c.A == 1) post_single_kernel<<<(c.N + 127) / 128, 128, 0, s>>>(c, st, sc, io);
+    else post_kernel<<<c.N, POST_THREADS, 0, s>>>(c, st, sc, io);
 }
 
 void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {

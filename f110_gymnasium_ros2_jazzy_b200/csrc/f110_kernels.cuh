@@ -17,7 +17,8 @@ struct MapView {
     int H, W;
     int last;           // (H-1)*W + (W-1): the cell numba's negative-index wrap lands on
     double res;         // metres per cell
-    double inv_res;     // 1/res, only used for the guarded fast cell index
+    double inv20;       // 2^20 / res: quotient in 2^-20 cell units for the guarded fast cell index
+    unsigned long long w20, h20;   // W << 20, H << 20
     double ox, oy, oc, os;
     double wres, hres;  // W*res, H*res
 };
@@ -73,6 +74,6 @@ struct SimConst {
 
 void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s);
 void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
-                  bool count_lookups, cudaStream_t s);
+                  bool count_lookups, int threads_per_block, cudaStream_t s);
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s);
 void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s);
