@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libf110_b200.so")
+LIB_PATH = os.environ.get("F110_B200_LIB") or os.path.join(_HERE, "csrc", "libf110_b200.so")   # env override: tuning builds only
 
 F110_ABI_VERSION = 1
 F110_NUM_PARAMS = 18

@@ -92,6 +92,12 @@ void layout_scratch(Arena& a, StepScratch& sc, int NA, int B) {
     sc.lookups = a.take<unsigned long long>(2);
     sc.stats = a.take<double>(F110_NUM_STATS);
     sc.scan = a.take<double>((size_t)NA * B);
+    sc.num_units = (unsigned)(((size_t)NA * B + 31) / 32);
+    sc.front_units = ((sc.num_units / 8 + 3) / 4) * 4 + 4;
+    sc.order_epoch = a.take<unsigned>(1);
+    sc.heavy_cnt = a.take<unsigned>(2);
+    sc.heavy_list = a.take<unsigned>(2 * (size_t)sc.front_units);
+    sc.unit_heavy = a.take<uint8_t>(2 * (size_t)sc.num_units);
 }
 
 struct Guard {   // selects the handle's device for the duration of a call
@@ -123,7 +129,7 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
     launch_post(sim->c, sim->st, sim->sc, io, s);
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
-    sim->launches += 3;
+    sim->launches += 4;
     CUDA_TRY(cudaPeekAtLastError());
     return F110_OK;
 }
@@ -161,7 +167,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
     if (const char* e = getenv("F110_LIDAR_THREADS")) {   // tuning knob, multiple of 32 in [32, 256]
         const int t = atoi(e);
-        if (t >= 32 && t <= 256 && t % 32 == 0) sim->lidar_threads = t;
+        if (t >= 32 && t <= 128 && t % 32 == 0) sim->lidar_threads = t;
     }
 
     Arena measure;

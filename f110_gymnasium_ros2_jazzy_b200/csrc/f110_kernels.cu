@@ -256,6 +256,13 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
     sc.ttc_hit[s] = 0;
 }
 
+// flips the lidar launch-order double buffer once per step (stream-ordered before the lidar kernel)
+__global__ void order_flip_kernel(StepScratch sc) {
+    const unsigned e = *sc.order_epoch + 1u;
+    *sc.order_epoch = e;
+    sc.heavy_cnt[(e & 1u) ^ 1u] = 0u;
+}
+
 // Simulator.reset alone (base_classes.py:627-643): poses only, no step, env bookkeeping untouched
 __global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restrict__ poses, const uint8_t* __restrict__ mask) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,7 +297,7 @@ __device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double 
 // fl(x*inv)*2^20 == fl(x*(inv*2^20)) because scaling by a power of two commutes with rounding.  Its error
 // against the true quotient is < 2.3e-16 relative (< 0.004 units for maps up to 2^24 cells), and the
 // reference's own rounded quotient is within half an ulp of the true one, so whenever the 20 fractional bits
-// are at least GUARD units away from both cell edges, trunc(q) is exactly the reference's int(x_rot/res) and
+// are at least GUARD units away from both cell edges, floor(q) is exactly the reference's int(x_rot/res) and
 // (0 <= q < W) is exactly its in-map test.  Everything else (cell edges, map border, negative, NaN, huge)
 // takes the exact path.
 template <bool IDENT>
@@ -304,15 +311,15 @@ __device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y
         x_rot = x_trans * m.oc + y_trans * m.os;
         y_rot = -x_trans * m.os + y_trans * m.oc;
     }
-    const long long ix = __double2ll_rz(x_rot * m.inv20);
-    const long long iy = __double2ll_rz(y_rot * m.inv20);
+    // negative inputs become huge unsigned values and fail the range test; NaN converts to 0 and fails the guard
+    const unsigned long long ux = (unsigned long long)__double2ll_rz(x_rot * m.inv20);
+    const unsigned long long uy = (unsigned long long)__double2ll_rz(y_rot * m.inv20);
     constexpr unsigned GUARD = 2u, FRAC = 0xFFFFFu;
-    const unsigned fx = ((unsigned)ix & FRAC) - GUARD;
-    const unsigned fy = ((unsigned)iy & FRAC) - GUARD;
+    const unsigned fx = ((unsigned)ux & FRAC) - GUARD;
+    const unsigned fy = ((unsigned)uy & FRAC) - GUARD;
     int idx;
-    if (fx <= FRAC - 2u * GUARD && fy <= FRAC - 2u * GUARD &&
-        (unsigned long long)ix < m.w20 && (unsigned long long)iy < m.h20) {
-        idx = (int)(iy >> 20) * m.W + (int)(ix >> 20);
+    if (fx <= FRAC - 2u * GUARD && fy <= FRAC - 2u * GUARD && ux < m.w20 && uy < m.h20) {
+        idx = (int)(uy >> 20) * m.W + (int)(ux >> 20);
     } else {
         idx = cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last);
     }
@@ -347,12 +354,41 @@ __device__ __forceinline__ float obs_lidar(double range, float lm) {
     return rf / lm;
 }
 
+#ifndef HEAVY_ITERS
+#define HEAVY_ITERS 48u
+#endif
+#ifndef LIDAR_MAX_THREADS
+#define LIDAR_MAX_THREADS 128
+#endif
+#ifndef LIDAR_MIN_BLOCKS
+#define LIDAR_MIN_BLOCKS 12
+#endif
 // COUNT : count dt lookups (roofline L-bar)            IDENT : map origin yaw == 0
 // DIRECT: A == 1, no opponent ray-cast can follow, so the scan goes straight to the caller's buffers
 template <bool COUNT, bool IDENT, bool DIRECT>
-__global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
+__global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
     const unsigned total = (unsigned)c.NA * (unsigned)c.B;
-    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    // ---- work-unit selection (one unit = 32 consecutive rays = one warp).  Ray lengths are heavy-tailed (median 4
+    // lookups, p99 42, max ~300 on the Shanghai map), so a long ray that starts in the last wave of CTAs leaves
+    // most SMs idle while it finishes.  A ray's length changes little from one step to the next, so every warp
+    // records whether its unit was long (>= HEAVY_ITERS lookups) and the next step's grid runs those units FIRST,
+    // in a front region of sc.front_units warps; the remaining warps walk the units in natural order and skip the
+    // ones the front region took.  Only the launch order depends on this history, never a result.
+    const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned cur = *sc.order_epoch & 1u, nxt = cur ^ 1u;
+    unsigned unit;
+    if (gwarp < sc.front_units) {
+        unsigned nheavy = sc.heavy_cnt[cur];
+        nheavy = nheavy < sc.front_units ? nheavy : sc.front_units;
+        if (gwarp >= nheavy) return;
+        unit = sc.heavy_list[cur * sc.front_units + gwarp];
+    } else {
+        unit = gwarp - sc.front_units;
+        if (unit >= sc.num_units) return;
+        if (sc.unit_heavy[cur * sc.num_units + unit]) return;
+    }
+    const unsigned r = unit * 32u + lane;
     unsigned nlook = 0;
     bool live = r < total;
     unsigned s = 0, i = 0;
@@ -387,13 +423,13 @@ __global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimSt
         const double eps = c.eps, max_range = c.max_range;
         double d = dt_lookup<IDENT>(m, x, y);
         double total_d = d;
-        if (COUNT) nlook = 1;
+        nlook = 1;
         while (d > eps && total_d <= max_range) {
             x += d * cs;
             y += d * sn;
             d = dt_lookup<IDENT>(m, x, y);
             total_d += d;
-            if (COUNT) ++nlook;
+            ++nlook;
         }
         if (total_d > max_range) total_d = max_range;
 
@@ -418,14 +454,30 @@ __global__ void __launch_bounds__(256) lidar_kernel(SimConst c, MapView m, SimSt
         const double vel = st.x[3][s];
         if (vel != 0.0) {
             const double proj_vel = vel * __ldg(c.beam_cos + i);
-            const double ttc = (range - __ldg(c.side_dist + i)) / proj_vel;
-            if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
+            const double num = range - __ldg(c.side_dist + i);
+            // |ttc| > 2*thresh whenever num > 2*thresh*|proj_vel|: then ttc is either >= thresh or negative and the
+            // exact quotient need not be formed (the negation keeps NaNs on the exact path)
+            if (!(num > 2.0 * c.ttc_thresh * fabs(proj_vel))) {
+                const double ttc = num / proj_vel;
+                if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
+            }
         }
+    }
+    // ---- history for the next step's launch order
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, nlook);
+    if (lane == 0) {
+        bool heavy = wmax >= HEAVY_ITERS;
+        if (heavy) {
+            const unsigned slot = atomicAdd(sc.heavy_cnt + nxt, 1u);
+            if (slot < sc.front_units) sc.heavy_list[nxt * sc.front_units + slot] = unit;
+            else heavy = false;
+        }
+        sc.unit_heavy[nxt * sc.num_units + unit] = heavy ? 1 : 0;
     }
     if (COUNT) {
         const unsigned wsum = __reduce_add_sync(0xffffffffu, nlook);
         const unsigned wrays = __popc(__ballot_sync(0xffffffffu, live));
-        if ((threadIdx.x & 31) == 0 && wrays) {
+        if (lane == 0 && wrays) {
             atomicAdd(sc.lookups, (unsigned long long)wsum);
             atomicAdd(sc.lookups + 1, (unsigned long long)wrays);
         }
@@ -798,6 +850,7 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
 
 void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     const int threads = 128;
+    order_flip_kernel<<<1, 1, 0, s>>>(sc);
     dynamics_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, sc, io);
 }
 
@@ -810,9 +863,9 @@ static void launch_lidar_t(const SimConst& c, const MapView& m, const SimState& 
 
 void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
                   bool count_lookups, int threads_per_block, cudaStream_t s) {
-    const unsigned total = (unsigned)c.NA * (unsigned)c.B;
     const unsigned threads = (unsigned)threads_per_block;
-    const unsigned blocks = (total + threads - 1) / threads;
+    const unsigned warps = sc.front_units + sc.num_units;
+    const unsigned blocks = (warps * 32u + threads - 1) / threads;
     const bool ident = (m.oc == 1.0 && m.os == 0.0);
     if (count_lookups) {
         if (ident) launch_lidar_t<true, true>(c, m, st, sc, io, blocks, threads, s);

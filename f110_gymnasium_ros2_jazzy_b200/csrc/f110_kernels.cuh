@@ -54,6 +54,13 @@ struct StepScratch {
     double* scan;       // [NA][B] noisy map scan, before the opponent ray-cast
     unsigned long long* lookups;  // [2] dt lookups, rays (only with F110_FLAG_COUNT_LOOKUPS)
     double* stats;      // [F110_NUM_STATS]
+    // launch-order history of the lidar kernel (see lidar_kernel): double-buffered by *order_epoch & 1
+    unsigned num_units;        // ceil(NA*B / 32) warp-sized work units
+    unsigned front_units;      // capacity of the heavy-first front region (multiple of 4)
+    unsigned* order_epoch;     // [1]
+    unsigned* heavy_cnt;       // [2]
+    unsigned* heavy_list;      // [2][front_units]
+    uint8_t* unit_heavy;       // [2][num_units]
 };
 
 struct SimConst {
