@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunks", type=int, default=4, help="env chunks pipelined by the e2e host path")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     return ap.parse_args()
 
@@ -84,45 +85,60 @@ def action_stream(torch, steps, n, a, device, seed=1234):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~5 ms in a background thread while the timed
+    region runs (nvidia-smi -lms 200 would see one or two samples of a 40 ms region)."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML device through its PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(gpu_index), 'pci_bus_id') else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+            self.h = h or pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
         except Exception:
-            self.p = None
+            self._t = None
+
+    def _loop(self):
+        nv = self.nv
+        masks = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, m in masks.items():
+                    if r & m:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._t is None:
             return out
-        time.sleep(0.25)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        self._t.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=float(np.median(self.samples)), reasons=sorted(self.reasons), samples=len(self.samples))
         return out
 
 
@@ -268,6 +284,20 @@ def main():
         dev_ms = float(t.item())
     stats = EpisodeStats().reduce(env.backend.stats())   # the path's only collective, off the step path
 
+    # ---- e2e on every rank: host buffers in and out through f110_step_host_async/f110_host_sync
+    e2e = None
+    if not args.no_e2e:
+        el = e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch)
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": total_envs * K / el, "unit": "env-steps/s", "h2d_bytes_per_step": E * A * 2 * 4 + E + E * A * 3 * 8,
+               "d2h_bytes_per_step": E * (B + 8) * 4 + E * 4 + E, "ms_per_step": 1e3 * el / K, "n_gpus": world,
+               "api": "F110HostVecEnv.step -> f110_step_host_async + f110_host_sync (C ABI, pinned host buffers, %d chunks)" % args.host_chunks,
+               "bytes_are": "per GPU"}
+
     value = total_envs * K / (dev_ms * 1e-3)
     rays_per_s = value * A * B
 
@@ -295,10 +325,6 @@ def main():
                     "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar,
                     "bytes_per_ray": bytes_per_ray, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                     "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]}}
-        # ---- e2e through the host-buffer C ABI call (f110_step_host): pinned H2D actions, D2H obs/reward/terminated
-        e2e = None
-        if not args.no_e2e:
-            e2e = e2e_run(env, acts, W, K, E, A, B, torch)
         # ---- CPU arm beside it
         cpu = None
         if not args.no_cpu_baseline:
@@ -347,24 +373,24 @@ def kernel_breakdown(env, acts, first, n, flush, torch):
     return per[1], per
 
 
-def e2e_run(env, acts, W, K, E, A, B, torch):
-    """Same metric through f110_step_host: every step copies the actions from pinned host memory to the device and
-    the observation / reward / terminated arrays back, inside the timed region."""
-    hacts = acts.cpu().pin_memory()
-    hout = env.backend.host_out(('obs', 'reward', 'terminated'))
-    hposes = env.start_poses.cpu().numpy()
-    term = hout['terminated'].numpy()
+def e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch):
+    """Same workload through the host-buffer API: every step uploads the actions from pinned host memory and
+    downloads observation / reward / terminated into pinned host memory, inside the timed region (wall clock
+    around K synchronous steps).  Returns elapsed seconds."""
+    from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv
+    henv = F110HostVecEnv(E, chunks=args.host_chunks, map_arrays=map_arrays, num_agents=A, num_beams=B, device=local,
+                          noise_std=0.01)
+    hacts = acts.cpu().pin_memory().numpy()
+    henv.reset(poses)
     for k in range(min(W, 5)):
-        env.backend.step_host(hacts[k].numpy(), None, term, hposes, hout)
+        henv.step(hacts[k])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(W, W + K):
-        env.backend.step_host(hacts[k].numpy(), None, term, hposes, hout)
+        henv.step(hacts[k])
     el = time.perf_counter() - t0
-    h2d = E * A * 2 * 4 + E + E * A * 3 * 8
-    d2h = E * (B + 8) * 4 + E * 4 + E
-    return {"value": E * K / el, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": 1e3 * el / K, "api": "f110_step_host (C ABI, host buffers)", "n_gpus": 1}
+    henv.close()
+    return el
 
 
 def load_traffic():

@@ -8,7 +8,7 @@ Public surface
 """
 from .gym_compat import HAVE_GYMNASIUM, make, register
 from .simulator import Integrator, Simulator
-from .env import F110Env, F110VecEnv
+from .env import F110Env, F110HostVecEnv, F110VecEnv
 from .backend import ALL_OUTPUTS, FAST_OUTPUTS, BatchSim
 from .params import default_params
 from .dist import EpisodeStats, shard_range
@@ -19,5 +19,5 @@ try:
 except Exception:  # already registered
     pass
 
-__all__ = ['F110Env', 'F110VecEnv', 'Simulator', 'Integrator', 'BatchSim', 'make', 'default_params', 'shard_range',
+__all__ = ['F110Env', 'F110VecEnv', 'F110HostVecEnv', 'Simulator', 'Integrator', 'BatchSim', 'make', 'default_params', 'shard_range',
            'EpisodeStats', 'ALL_OUTPUTS', 'FAST_OUTPUTS', 'HAVE_GYMNASIUM']

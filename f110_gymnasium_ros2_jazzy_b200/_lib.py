@@ -21,7 +21,7 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 
 # every symbol include/f110_b200.h declares
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_tables",
-           "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host",
+           "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
            "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing"]
 
@@ -69,6 +69,8 @@ def load():
     L.f110_sim_reset.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.f110_step.argtypes = [vp, C.POINTER(F110StepIO), vp]
     L.f110_step_host.argtypes = [vp, C.POINTER(F110StepIO)]
+    L.f110_step_host_async.argtypes = [vp, C.POINTER(F110StepIO)]
+    L.f110_host_sync.argtypes = [vp]
     L.f110_state_nbytes.argtypes = [vp]
     L.f110_state_nbytes.restype = C.c_int64
     L.f110_get_state.argtypes = [vp, vp, vp]

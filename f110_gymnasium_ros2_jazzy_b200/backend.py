@@ -172,8 +172,9 @@ class BatchSim(object):
             return self.step(None, noise, mask, p, None)
         return self.step(None, noise, env_mask, p, env_mask)
 
-    def step_host(self, actions=None, noise=None, reset_mask=None, reset_poses=None, out=None):
-        """Host-buffer entry (f110_step_host): numpy in, numpy out, copies inside the call."""
+    def step_host(self, actions=None, noise=None, reset_mask=None, reset_poses=None, out=None, sync=True):
+        """Host-buffer entry (f110_step_host): numpy in, numpy out, copies inside the call.  With sync=False the
+        call only enqueues (f110_step_host_async); the buffers are valid after host_sync()."""
         N, A, B = self.N, self.A, self.B
         if out is None:
             out = self.host_out()
@@ -195,8 +196,15 @@ class BatchSim(object):
             return C.c_void_p(a.data_ptr()) if torch.is_tensor(a) else a.ctypes.data_as(C.c_void_p)
         io = _lib.F110StepIO(actions=hp(act), actions_f64=f64, noise=hp(nz), reset_mask=hp(rm), reset_poses=hp(rp),
                              active_mask=None, **{k: hp(out[k]) for k in out})
-        _lib.check(self.lib.f110_step_host(self.h, C.byref(io)))
+        self._keep_host = (act, nz, rm, rp, out)   # the async copies read / write these after we return
+        if sync:
+            _lib.check(self.lib.f110_step_host(self.h, C.byref(io)))
+        else:
+            _lib.check(self.lib.f110_step_host_async(self.h, C.byref(io)))
         return out
+
+    def host_sync(self):
+        _lib.check(self.lib.f110_host_sync(self.h))
 
     def host_out(self, outputs=None, pinned=True):
         """Pinned host tensors shaped like the outputs, for step_host."""

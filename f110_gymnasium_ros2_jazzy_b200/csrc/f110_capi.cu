@@ -312,7 +312,7 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream) {
     return run_step(sim, *io, (cudaStream_t)stream);
 }
 
-int f110_step_host(F110Sim* sim, const F110StepIO* hio) {
+int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     const int rc = check_step_io(sim, hio);
     if (rc != F110_OK) return rc;
     Guard g(sim->cfg.device);
@@ -365,8 +365,20 @@ int f110_step_host(F110Sim* sim, const F110StepIO* hio) {
     D2H(lap_counts, d_lc, NA * sizeof(double))
     D2H(time, d_time, N * sizeof(double))
 #undef D2H
-    CUDA_TRY(cudaStreamSynchronize(s));
     return F110_OK;
+}
+
+int f110_host_sync(F110Sim* sim) {
+    if (!sim) return fail(F110_ERR_INVALID, "null handle");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaStreamSynchronize(sim->host_stream));
+    return F110_OK;
+}
+
+int f110_step_host(F110Sim* sim, const F110StepIO* hio) {
+    const int rc = f110_step_host_async(sim, hio);
+    if (rc != F110_OK) return rc;
+    return f110_host_sync(sim);
 }
 
 int64_t f110_state_nbytes(const F110Sim* sim) { return sim ? (int64_t)sim->state_bytes : 0; }

@@ -235,3 +235,69 @@ class F110VecEnv(object):
 
     def close(self):
         self.backend.close()
+
+
+class F110HostVecEnv(object):
+    """N F110Envs for a HOST-side consumer: numpy actions in, pinned-host observations out, every step.
+
+    This is the end-to-end shape of the reference's own use (train_ddpg.py:160-202 reads the observation on the
+    host every step).  The envs are split over ``chunks`` independent library handles, each with its own stream;
+    a step enqueues, per chunk, the action upload, the three kernels and the observation download
+    (f110_step_host_async), then waits for all of them (f110_host_sync) -- so one chunk's PCIe traffic overlaps
+    the other chunks' kernels.  Auto-reset as in F110VecEnv.
+    """
+
+    def __init__(self, num_envs, chunks=4, map_arrays=None, map_dir=None, map=None, map_ext='.png', num_agents=1,
+                 seed=42, device=None, outputs=FAST_OUTPUTS, num_beams=1080, **kw):
+        chunks = max(1, min(chunks, num_envs))
+        self.num_envs, self.num_agents, self.num_beams = num_envs, num_agents, num_beams
+        self.bounds = [(num_envs * k) // chunks for k in range(chunks + 1)]
+        self.parts = []
+        for k in range(chunks):
+            n = self.bounds[k + 1] - self.bounds[k]
+            b = BatchSim(n, num_agents, seed=seed + 7919 * k, device=device, outputs=('obs',), num_beams=num_beams, **kw)
+            if map_arrays is not None:
+                b.set_map_arrays(*map_arrays)
+            else:
+                b.set_map(map_dir + map + '.yaml', map_ext)
+            self.parts.append(b)
+        outs = tuple(dict.fromkeys(tuple(outputs) + ('obs', 'reward', 'terminated')))
+        self.out = {}
+        from .backend import _OUT_SPECS
+        for key in outs:
+            shape, dtype = _OUT_SPECS[key]
+            self.out[key] = torch.zeros(shape(num_envs, num_agents, num_beams), dtype=dtype, pin_memory=True)
+        self._views = [{key: t[self.bounds[k]:self.bounds[k + 1]] for key, t in self.out.items()} for k in range(chunks)]
+        self.start_poses = None
+        self._term_t = torch.ones(num_envs, dtype=torch.uint8, pin_memory=True)
+        self._term = self._term_t.numpy()
+
+    def _run(self, actions, reset_mask):
+        for k, b in enumerate(self.parts):
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            b.step_host(None if actions is None else actions[lo:hi], None, reset_mask[lo:hi], self.start_poses[lo:hi],
+                        self._views[k], sync=False)
+        for b in self.parts:
+            b.host_sync()
+        return self.out
+
+    def reset(self, poses):
+        p = np.asarray(poses, np.float64)
+        if p.ndim == 2:
+            p = np.broadcast_to(p[None], (self.num_envs,) + p.shape)
+        self._poses_t = torch.from_numpy(np.ascontiguousarray(p)).pin_memory()
+        self.start_poses = self._poses_t.numpy()
+        self._term[:] = 1
+        o = self._run(None, self._term)
+        return o['obs'].numpy(), o
+
+    def step(self, actions):
+        """actions: numpy (or pinned tensor viewed as numpy) [N, A, 2] f32/f64."""
+        # the previous step's `terminated` (still in the pinned output buffer) is this step's reset mask
+        np.copyto(self._term, self.out['terminated'].numpy())
+        o = self._run(actions, self._term)
+        return o['obs'].numpy(), o['reward'].numpy(), o['terminated'].numpy(), None, o
+
+    def close(self):
+        for b in self.parts:
+            b.close()

@@ -148,6 +148,10 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream);
 
 /* Same contract with HOST pointers in `io`; copies in and out on an internal stream and synchronises it. */
 int f110_step_host(F110Sim* sim, const F110StepIO* io);
+/* The same without the final synchronisation: the host buffers are valid after f110_host_sync().  Lets a caller
+ * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels. */
+int f110_step_host_async(F110Sim* sim, const F110StepIO* io);
+int f110_host_sync(F110Sim* sim);
 
 /* Checkpoint of the whole persistent simulation state as one opaque blob (DEVICE pointer). */
 int64_t f110_state_nbytes(const F110Sim* sim);

@@ -303,3 +303,63 @@ def test_step_host_matches_device_path():
         h = b2.sim.step_host(act, noise)
     for k in ('obs', 'state', 'scans_f64', 'terminated', 'collisions'):
         assert np.array_equal(d[k], h[k].numpy()), k
+
+
+def test_host_vec_env_matches_device_vec_env():
+    """F110HostVecEnv (chunked f110_step_host_async pipeline) == one F110VecEnv batch, noise off, auto-reset on."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv, F110VecEnv
+    N = 96
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
+    dev = F110VecEnv(N, num_agents=1, map_arrays=m, noise_std=0.0)
+    host = F110HostVecEnv(N, chunks=3, map_arrays=m, num_agents=1, noise_std=0.0)
+    rng = np.random.default_rng(11)
+    od, _ = dev.reset(poses)
+    oh, _ = host.reset(poses)
+    torch.cuda.synchronize()
+    assert np.array_equal(od.cpu().numpy(), oh)
+    terms = 0
+    for t in range(150):
+        act = rng.uniform([-0.4189, 0], [0.4189, 20], size=(N, 1, 2)).astype(np.float32)
+        od, rd, td, _, _ = dev.step(torch.from_numpy(act).cuda())
+        oh, rh, th, _, _ = host.step(act)
+        torch.cuda.synchronize()
+        assert np.array_equal(td.cpu().numpy(), th), t
+        assert np.array_equal(od.cpu().numpy(), oh), t
+        terms += int(th.sum())
+    assert terms > 0      # the auto-reset path was exercised
+    host.close(); dev.close()
+
+
+def test_step_is_cuda_graph_capturable():
+    """f110_step neither allocates nor synchronises: a step can be captured and replayed by torch.cuda.graph."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+    N = 64
+    m = H.golden_map('open_square')
+    a = BatchSim(N, 2, outputs=ALL_OUTPUTS, noise_std=0.0); a.set_map_arrays(*m)
+    b = BatchSim(N, 2, outputs=ALL_OUTPUTS, noise_std=0.0); b.set_map_arrays(*m)
+    rng = np.random.default_rng(2)
+    poses = np.zeros((N, 2, 3)); poses[:, 1, 0] = 2.5; poses[:, :, 1] = rng.uniform(-4, 4, size=(N, 1))
+    a.reset(poses); b.reset(poses)
+    act = torch.zeros((N, 2, 2), dtype=torch.float32, device='cuda')
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        b.step(act)                       # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    sd = b.state_dict()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        b.step(act)
+    b.load_state_dict(sd)                 # undo the capture-time bookkeeping and the warm-up step
+    a.step(act)
+    for t in range(20):
+        act.copy_(torch.from_numpy(rng.uniform([-0.4, 0], [0.4, 8], size=(N, 2, 2)).astype(np.float32)))
+        a.step(act)
+        g.replay()
+    torch.cuda.synchronize()
+    for k in a.out:
+        assert torch.equal(a.out[k], b.out[k]), k

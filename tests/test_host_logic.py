@@ -1,0 +1,154 @@
+"""CPU suite for the host side: map/param tables, the gym shim, env-index sharding and the gloo all-reduce of the
+episode statistics (world_size 2), and that the C-ABI library loads and exports every declared symbol.
+No compute call is made without a GPU."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    L = _lib.load()
+    hdr = open(os.path.join(ROOT, 'include', 'f110_b200.h')).read()
+    declared = set(re.findall(r'\b(f110_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.f110_abi_version() == _lib.F110_ABI_VERSION
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from f110_gymnasium_ros2_jazzy_b200 import BatchSim
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchSim(1)
+    # and the C entry point itself refuses
+    import ctypes as C
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    from f110_gymnasium_ros2_jazzy_b200.params import default_params, params_vector
+    L = _lib.load()
+    cfg = _lib.F110Config(abi_version=_lib.F110_ABI_VERSION, device=0, num_envs=1, num_agents=1, num_beams=1080,
+                          theta_dis=2000, integrator=1, ego_idx=0, fov=4.7, eps=1e-4, max_range=30.0, timestep=0.01,
+                          ttc_thresh=0.005, lidar_max=30.0, noise_std=0.01, seed=1)
+    h = C.c_void_p()
+    pv = params_vector(default_params())
+    rc = L.f110_create(C.byref(cfg), pv.ctypes.data_as(C.c_void_p), C.byref(h))
+    assert rc == _lib.F110_ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in L.f110_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'f110_gymnasium_ros2_jazzy_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.lower().replace('the oracle', ''), os.path.join(dirpath, f)
+
+
+def test_tables_match_reference_tables():
+    from f110_gymnasium_ros2_jazzy_b200.params import beam_tables, default_params, theta_tables
+    s, c, a, bc, sd = H.tables()
+    ms, mc = theta_tables(2000)
+    ma, mbc, msd = beam_tables(default_params(), 1080, 4.7)
+    # numpy's sin/cos may differ from the recording machine's by an ulp on another CPU: allow 2 ulp
+    for mine, ref in ((ms, s), (mc, c), (ma, a), (mbc, bc), (msd, sd)):
+        assert np.allclose(mine, ref, rtol=0, atol=5e-16 * max(1.0, np.abs(ref).max()))
+    assert np.array_equal(ma, a)
+
+
+def test_map_loader_reproduces_reference_dt(tmp_path):
+    from f110_gymnasium_ros2_jazzy_b200.maps import load_map, map_bounds
+    for name in ('straight_corridor', 'open_square'):
+        d, n = H.write_map_files(name, str(tmp_path))
+        dt, res, origin = load_map(d + n + '.yaml', '.png')
+        gdt, gres, gorigin = H.golden_map(name)
+        assert np.array_equal(dt, gdt) and res == gres and origin == gorigin
+        x0, x1, y0, y1 = map_bounds(d + n + '.yaml', d)
+        assert x1 > x0 and y1 > y0
+
+
+def test_gym_shim_surface():
+    from f110_gymnasium_ros2_jazzy_b200 import gym_compat as g
+    box = g.spaces.Box(low=np.zeros((2, 2), np.float32), high=np.ones((2, 2), np.float32), dtype=np.float32)
+    x = box.sample()
+    assert x.shape == (2, 2) and x.dtype == np.float32 and box.contains(x)
+    with pytest.raises(ValueError):
+        g.make('nope-v0')
+
+
+def test_shard_range_partitions():
+    from f110_gymnasium_ros2_jazzy_b200 import shard_range
+    for n in (1, 7, 4096, 262144):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _stats_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from f110_gymnasium_ros2_jazzy_b200.dist import EpisodeStats, shard_range
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = shard_range(10, rank, world)
+    local = torch.zeros(8, dtype=torch.float64)
+    local[0] = hi - lo            # episodes
+    local[1] = 100.0 * (hi - lo)  # steps
+    local[2] = rank
+    out = EpisodeStats().reduce(local)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_episode_stats_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert res[r]['episodes'] == 10.0 and res[r]['episode_steps'] == 1000.0 and res[r]['ego_collisions'] == 1.0
+        assert res[r]['mean_episode_steps'] == 100.0
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference must work without a GPU and print one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2',
+                                   '--warmup', '1', '--cpu-envs', '16'], cwd=ROOT, timeout=300)
+    line = json.loads(out.decode().strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'env-steps/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
