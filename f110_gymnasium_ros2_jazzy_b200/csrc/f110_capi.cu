@@ -92,12 +92,22 @@ void layout_scratch(Arena& a, StepScratch& sc, int NA, int B) {
     sc.lookups = a.take<unsigned long long>(2);
     sc.stats = a.take<double>(F110_NUM_STATS);
     sc.scan = a.take<double>((size_t)NA * B);
-    sc.num_units = (unsigned)(((size_t)NA * B + 31) / 32);
+    sc.num_units = (unsigned)((((size_t)NA * B + 31) / 32 + 3) / 4 * 4);
     sc.front_units = ((sc.num_units / 8 + 3) / 4) * 4 + 4;
-    sc.order_epoch = a.take<unsigned>(1);
     sc.heavy_cnt = a.take<unsigned>(2);
     sc.heavy_list = a.take<unsigned>(2 * (size_t)sc.front_units);
     sc.unit_heavy = a.take<uint8_t>(2 * (size_t)sc.num_units);
+}
+
+FastDiv make_fast_div(uint32_t d) {
+    // Granlund & Montgomery: l = ceil(log2 d), mul = floor(2^32 (2^l - d) / d) + 1, sh1 = min(l, 1), sh2 = max(l - 1, 0)
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    FastDiv f;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 0 ? l - 1 : 0;
+    return f;
 }
 
 struct Guard {   // selects the handle's device for the duration of a call
@@ -129,7 +139,7 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
     launch_post(sim->c, sim->st, sim->sc, io, s);
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
-    sim->launches += 4;
+    sim->launches += 3;
     CUDA_TRY(cudaPeekAtLastError());
     return F110_OK;
 }
@@ -200,6 +210,8 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     c.fov = cfg->fov; c.eps = cfg->eps; c.max_range = cfg->max_range; c.timestep = cfg->timestep;
     c.lidar_dist = cfg->lidar_dist; c.ttc_thresh = cfg->ttc_thresh; c.noise_std = cfg->noise_std;
     c.lidar_max = (float)cfg->lidar_max; c.seed = cfg->seed;
+    c.noise_key = (uint32_t)cfg->seed ^ ((uint32_t)(cfg->seed >> 32) * 0x85EBCA6Bu) ^ 0x46313130u;
+    c.div_B = make_fast_div((uint32_t)B); c.div_A = make_fast_div((uint32_t)A);
     // ScanSimulator2D.__init__ laser_models.py:367-368
     const double angle_increment = cfg->fov / (B - 1);
     c.theta_inc = cfg->theta_dis * angle_increment / (2. * F110_PI);
@@ -239,8 +251,8 @@ void f110_destroy(F110Sim* sim) {
 int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
                  double orig_x, double orig_y, double orig_cos, double orig_sin) {
     if (!sim || !dt || height < 1 || width < 1 || !(resolution > 0)) return fail(F110_ERR_INVALID, "bad map arguments");
-    if ((double)height * width >= 2147483648.0 || height > (1 << 24) || width > (1 << 24))
-        return fail(F110_ERR_INVALID, "map too large (need H*W < 2^31 and H, W <= 2^24)");
+    if ((double)height * width >= 2147483648.0 || height >= 65536 || width >= 65536)
+        return fail(F110_ERR_INVALID, "map too large (need H*W < 2^31 and H, W < 65536)");
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
     double* d = nullptr;
@@ -252,8 +264,8 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
     sim->d_map = d;
     MapView& m = sim->map;
     m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; m.inv20 = (1.0 / resolution) * 1048576.0;
-    m.w20 = (unsigned long long)width << 20; m.h20 = (unsigned long long)height << 20;
+    m.res = resolution; m.inv16 = (1.0 / resolution) * 65536.0;
+    m.w16 = (unsigned)width << 16; m.h16 = (unsigned)height << 16;
     m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
     m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
     sim->map_set = true;

@@ -143,6 +143,16 @@ __device__ __forceinline__ void pid(double speed, double steer, double cur_speed
 
 __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        // Publish the launch-order history the lidar kernel recorded during the previous step (the "next" halves
+        // of the buffers; its length was latched into heavy_cnt[0] by the post kernel) as this step's order.  A copy
+        // rather than a pointer flip, so a captured CUDA graph stays valid step after step.
+        const unsigned stride = gridDim.x * blockDim.x;
+        for (unsigned k = s; k < sc.num_units / 4; k += stride)   // num_units is padded to a multiple of 4
+            reinterpret_cast<uint32_t*>(sc.unit_heavy)[k] = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units)[k];
+        const unsigned n = sc.heavy_cnt[0];
+        for (unsigned k = s; k < n; k += stride) sc.heavy_list[k] = sc.heavy_list[sc.front_units + k];
+    }
     if (s >= c.NA) return;
     const int env = s / c.A;
     const int a = s - env * c.A;
@@ -256,13 +266,6 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
     sc.ttc_hit[s] = 0;
 }
 
-// flips the lidar launch-order double buffer once per step (stream-ordered before the lidar kernel)
-__global__ void order_flip_kernel(StepScratch sc) {
-    const unsigned e = *sc.order_epoch + 1u;
-    *sc.order_epoch = e;
-    sc.heavy_cnt[(e & 1u) ^ 1u] = 0u;
-}
-
 // Simulator.reset alone (base_classes.py:627-643): poses only, no step, env bookkeeping untouched
 __global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restrict__ poses, const uint8_t* __restrict__ mask) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,13 +296,13 @@ __device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double 
     return idx;
 }
 
-// Cell index without the two fp64 divisions.  q20 = x_rot * (2^20 / res) is the quotient in 2^-20 cell units;
-// fl(x*inv)*2^20 == fl(x*(inv*2^20)) because scaling by a power of two commutes with rounding.  Its error
-// against the true quotient is < 2.3e-16 relative (< 0.004 units for maps up to 2^24 cells), and the
-// reference's own rounded quotient is within half an ulp of the true one, so whenever the 20 fractional bits
-// are at least GUARD units away from both cell edges, floor(q) is exactly the reference's int(x_rot/res) and
-// (0 <= q < W) is exactly its in-map test.  Everything else (cell edges, map border, negative, NaN, huge)
-// takes the exact path.
+// Cell index without the two fp64 divisions.  q = x_rot * (2^16 / res) is the quotient in 2^-16 cell units
+// (fl(x*inv)*2^16 == fl(x*(inv*2^16)): scaling by a power of two commutes with rounding).  Its error against
+// the true quotient is < 2.3e-16 relative (< 1e-6 units for maps up to 2^16 cells wide), and the reference's own
+// rounded quotient is within half an ulp of the true one, so whenever the 16 fractional bits are at least one
+// unit away from both cell edges, trunc(q) >> 16 is exactly the reference's int(x_rot/res) and (q < W << 16) is
+// exactly its in-map test.  Everything else -- the 2/65536 of lookups next to a cell edge, the map border, negative
+// (converts to 0), NaN (0) and huge (0xFFFFFFFF) coordinates -- takes the exact path.
 template <bool IDENT>
 __device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y) {
     const double x_trans = x - m.ox;
@@ -311,29 +314,26 @@ __device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y
         x_rot = x_trans * m.oc + y_trans * m.os;
         y_rot = -x_trans * m.os + y_trans * m.oc;
     }
-    // negative inputs become huge unsigned values and fail the range test; NaN converts to 0 and fails the guard
-    const unsigned long long ux = (unsigned long long)__double2ll_rz(x_rot * m.inv20);
-    const unsigned long long uy = (unsigned long long)__double2ll_rz(y_rot * m.inv20);
-    constexpr unsigned GUARD = 2u, FRAC = 0xFFFFFu;
-    const unsigned fx = ((unsigned)ux & FRAC) - GUARD;
-    const unsigned fy = ((unsigned)uy & FRAC) - GUARD;
+    const unsigned ux = __double2uint_rz(x_rot * m.inv16);
+    const unsigned uy = __double2uint_rz(y_rot * m.inv16);
+    // (f - 1) <= 65533  <=>  1 <= f <= 65534 for the 16-bit fraction f
     int idx;
-    if (fx <= FRAC - 2u * GUARD && fy <= FRAC - 2u * GUARD && ux < m.w20 && uy < m.h20) {
-        idx = (int)(uy >> 20) * m.W + (int)(ux >> 20);
+    if (((ux & 0xFFFFu) - 1u) <= 0xFFFDu && ((uy & 0xFFFFu) - 1u) <= 0xFFFDu && ux < m.w16 && uy < m.h16) {
+        idx = (int)(uy >> 16) * m.W + (int)(ux >> 16);
     } else {
         idx = cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last);
     }
     return __ldg(m.dt + idx);
 }
 
-// Philox4x32-10 (Salmon et al. 2011), counter-based: no per-ray generator state in HBM
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+// Philox2x32-10 (Salmon et al. 2011), counter-based: no per-ray generator state in HBM.  One call yields the
+// 64 bits one Box-Muller sample needs, at half the integer multiplies of Philox4x32.
+__device__ __forceinline__ uint2 philox2x32_10(uint2 ctr, uint32_t key) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+        const uint32_t hi = __umulhi(0xD256D193u, ctr.x), lo = 0xD256D193u * ctr.x;
+        ctr = make_uint2(hi ^ key ^ ctr.y, lo);
+        key += 0x9E3779B9u;
     }
     return ctr;
 }
@@ -342,6 +342,12 @@ __device__ __forceinline__ float gaussian_from_bits(uint32_t a, uint32_t b) {
     const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
     const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
     return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
+}
+
+// n / d for a run-time d through the multiply-shift pair the host precomputed (Granlund & Montgomery 1994)
+__device__ __forceinline__ unsigned fast_div(unsigned n, FastDiv d) {
+    const unsigned t = __umulhi(n, d.mul);
+    return (t + ((n - t) >> d.sh1)) >> d.sh2;
 }
 
 // _pack_flat_obs lidar channel, f110_env.py:557-560
@@ -372,30 +378,29 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
     // lookups, p99 42, max ~300 on the Shanghai map), so a long ray that starts in the last wave of CTAs leaves
     // most SMs idle while it finishes.  A ray's length changes little from one step to the next, so every warp
     // records whether its unit was long (>= HEAVY_ITERS lookups) and the next step's grid runs those units FIRST,
-    // in a front region of sc.front_units warps; the remaining warps walk the units in natural order and skip the
+    // in a front region of sc.front_units warps (order_publish_kernel hands the history over); the remaining warps walk the units in natural order and skip the
     // ones the front region took.  Only the launch order depends on this history, never a result.
     const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned cur = *sc.order_epoch & 1u, nxt = cur ^ 1u;
     unsigned unit;
     if (gwarp < sc.front_units) {
-        unsigned nheavy = sc.heavy_cnt[cur];
-        nheavy = nheavy < sc.front_units ? nheavy : sc.front_units;
-        if (gwarp >= nheavy) return;
-        unit = sc.heavy_list[cur * sc.front_units + gwarp];
+        if (gwarp >= sc.heavy_cnt[0]) return;
+        unit = sc.heavy_list[gwarp];
     } else {
         unit = gwarp - sc.front_units;
         if (unit >= sc.num_units) return;
-        if (sc.unit_heavy[cur * sc.num_units + unit]) return;
+        if (sc.unit_heavy[unit]) return;
     }
     const unsigned r = unit * 32u + lane;
     unsigned nlook = 0;
     bool live = r < total;
     unsigned s = 0, i = 0;
+    unsigned env = 0;
     if (live) {
-        s = r / (unsigned)c.B;
+        s = fast_div(r, c.div_B);
         i = r - s * (unsigned)c.B;
-        if (io.active_mask && !io.active_mask[s / (unsigned)c.A]) live = false;
+        env = DIRECT ? s : fast_div(s, c.div_A);
+        if (io.active_mask && !io.active_mask[env]) live = false;
     }
     if (live) {
         // beam direction: closed form of the reference's running sum theta_index += increment with wrap
@@ -438,8 +443,9 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
         if (io.noise) {
             range += io.noise[r];
         } else if (c.noise_std > 0.0) {
-            const uint4 bits = philox4x32_10(make_uint4(i, st.step_count[s / (unsigned)c.A], s, 0x46313130u),
-                                             make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+            // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
+            // reset (base_classes.py:204), the stream restarts with every episode; unlike it, every ray has its own
+            const uint2 bits = philox2x32_10(make_uint2(r, st.step_count[env]), c.noise_key);
             range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
         }
         if (DIRECT) {
@@ -468,11 +474,11 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
     if (lane == 0) {
         bool heavy = wmax >= HEAVY_ITERS;
         if (heavy) {
-            const unsigned slot = atomicAdd(sc.heavy_cnt + nxt, 1u);
-            if (slot < sc.front_units) sc.heavy_list[nxt * sc.front_units + slot] = unit;
+            const unsigned slot = atomicAdd(sc.heavy_cnt + 1, 1u);
+            if (slot < sc.front_units) sc.heavy_list[sc.front_units + slot] = unit;
             else heavy = false;
         }
-        sc.unit_heavy[nxt * sc.num_units + unit] = heavy ? 1 : 0;
+        sc.unit_heavy[sc.num_units + unit] = heavy ? 1 : 0;
     }
     if (COUNT) {
         const unsigned wsum = __reduce_add_sync(0xffffffffu, nlook);
@@ -485,6 +491,13 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
 }
 
 // ---------------------------------------------------------------- K3: post
+
+// the lidar kernel of this step is complete: latch how many heavy units it recorded and re-arm the counter
+__device__ __forceinline__ void latch_launch_order(const StepScratch& sc) {
+    const unsigned n = sc.heavy_cnt[1];
+    sc.heavy_cnt[0] = n < sc.front_units ? n : sc.front_units;
+    sc.heavy_cnt[1] = 0u;
+}
 
 // get_trmtx + get_vertices, collision_models.py:218-260; order rl, rr, fr, fl
 __device__ __forceinline__ void get_vertices(double px, double py, double yaw, double length, double width, double* v) {
@@ -611,6 +624,7 @@ constexpr int POST_THREADS = 256;
 
 __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     const int env = blockIdx.x;
+    if (env == 0 && threadIdx.x == 0) latch_launch_order(sc);
     if (io.active_mask && !io.active_mask[env]) return;
     const int A = c.A, B = c.B;
     const int tid = threadIdx.x;
@@ -790,6 +804,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
 // per env applies the iTTC consequence and the finish-zone / done bookkeeping (same statements as post_kernel).
 __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env == 0) latch_launch_order(sc);
     if (env >= c.N) return;
     if (io.active_mask && !io.active_mask[env]) return;
     const int s = env;
@@ -850,7 +865,6 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
 
 void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     const int threads = 128;
-    order_flip_kernel<<<1, 1, 0, s>>>(sc);
     dynamics_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, sc, io);
 }
 

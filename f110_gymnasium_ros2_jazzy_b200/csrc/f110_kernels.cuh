@@ -17,8 +17,8 @@ struct MapView {
     int H, W;
     int last;           // (H-1)*W + (W-1): the cell numba's negative-index wrap lands on
     double res;         // metres per cell
-    double inv20;       // 2^20 / res: quotient in 2^-20 cell units for the guarded fast cell index
-    unsigned long long w20, h20;   // W << 20, H << 20
+    double inv16;       // 2^16 / res: quotient in 2^-16 cell units for the guarded fast cell index
+    unsigned w16, h16;  // W << 16, H << 16
     double ox, oy, oc, os;
     double wres, hres;  // W*res, H*res
 };
@@ -54,14 +54,15 @@ struct StepScratch {
     double* scan;       // [NA][B] noisy map scan, before the opponent ray-cast
     unsigned long long* lookups;  // [2] dt lookups, rays (only with F110_FLAG_COUNT_LOOKUPS)
     double* stats;      // [F110_NUM_STATS]
-    // launch-order history of the lidar kernel (see lidar_kernel): double-buffered by *order_epoch & 1
-    unsigned num_units;        // ceil(NA*B / 32) warp-sized work units
+    // launch-order history of the lidar kernel (see lidar_kernel): [0] = this step's order, [1] = being recorded
+    unsigned num_units;        // ceil(NA*B / 32) warp-sized work units, padded to a multiple of 4
     unsigned front_units;      // capacity of the heavy-first front region (multiple of 4)
-    unsigned* order_epoch;     // [1]
     unsigned* heavy_cnt;       // [2]
     unsigned* heavy_list;      // [2][front_units]
     uint8_t* unit_heavy;       // [2][num_units]
 };
+
+struct FastDiv { uint32_t mul, sh1, sh2; };   // n / d == (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(n, mul)
 
 struct SimConst {
     int N, A, B, NA;
@@ -70,6 +71,8 @@ struct SimConst {
     double theta_inc;   // theta_dis * (fov/(B-1)) / (2 pi)               laser_models.py:367-368
     float lidar_max;
     uint64_t seed;
+    uint32_t noise_key;  // Philox key derived from seed
+    FastDiv div_B, div_A;
     const double* params;      // [A][18]
     const double* sim_params;  // [18] Simulator.params (construction time; base_classes.py:562)
     const double* sines;       // [theta_dis]
