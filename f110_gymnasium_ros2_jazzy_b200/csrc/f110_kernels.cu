@@ -370,7 +370,7 @@ __device__ __forceinline__ float obs_lidar(double range, float lm) {
 #define LIDAR_MIN_BLOCKS 12
 #endif
 // COUNT : count dt lookups (roofline L-bar)            IDENT : map origin yaw == 0
-// DIRECT: A == 1, no opponent ray-cast can follow, so the scan goes straight to the caller's buffers
+// DIRECT: A == 1 (env == s, no opponent ray-cast can follow, no fp64 scratch copy of the scan)
 template <bool COUNT, bool IDENT, bool DIRECT>
 __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
     const unsigned total = (unsigned)c.NA * (unsigned)c.B;
@@ -448,12 +448,15 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
             const uint2 bits = philox2x32_10(make_uint2(r, st.step_count[env]), c.noise_key);
             range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
         }
+        // The scan goes straight to the caller's buffers.  With opponents (A >= 2) the post kernel lowers the few beams
+        // that hit another car afterwards, from the fp64 copy kept in scratch.
+        if (io.scans_f64) io.scans_f64[r] = range;
+        if (io.scans_f32) io.scans_f32[r] = (float)range;
         if (DIRECT) {
-            if (io.scans_f64) io.scans_f64[r] = range;
-            if (io.scans_f32) io.scans_f32[r] = (float)range;
             if (io.obs) io.obs[(size_t)s * (c.B + 8) + i] = obs_lidar(range, c.lidar_max);
         } else {
             sc.scan[r] = range;
+            if (io.obs && s == env * (unsigned)c.A) io.obs[(size_t)env * (c.B + 8) + i] = obs_lidar(range, c.lidar_max);
         }
 
         // check_ttc_jit, laser_models.py:205-213 (any-reduction; the reference's early break is irrelevant)
@@ -582,19 +585,25 @@ __device__ bool gjk_collision(const double* v1, const double* v2) {
     return false;
 }
 
-// index of the first minimum of |scan_angles[k] - a| over a strictly increasing table (np.argmin semantics)
+// index of the first minimum of |scan_angles[k] - a| over a strictly increasing table (np.argmin semantics).
+// |ang[k] - a| is V-shaped over a monotone table, so a local minimum is the global one: start from the index a
+// uniform table would give and walk; ties resolve to the lower index, as argmin does.
 __device__ __forceinline__ int nearest_beam(const double* __restrict__ ang, int B, double a) {
     if (a != a) return 0;
-    int lo = 0, hi = B;   // lower_bound: first k with ang[k] >= a
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(ang + mid) < a) lo = mid + 1; else hi = mid;
+    const double a0 = __ldg(ang), a1 = __ldg(ang + B - 1);
+    double g = (a - a0) / (a1 - a0) * (double)(B - 1);
+    g = g < 0. ? 0. : (g > (double)(B - 1) ? (double)(B - 1) : g);
+    int k = (int)(g + 0.5);
+    double dk = fabs(__ldg(ang + k) - a);
+    while (k + 1 < B) {
+        const double dn = fabs(__ldg(ang + k + 1) - a);
+        if (dn < dk) { ++k; dk = dn; } else break;
     }
-    if (lo == 0) return 0;
-    if (lo == B) return B - 1;
-    const double dl = fabs(__ldg(ang + lo - 1) - a);
-    const double dr = fabs(__ldg(ang + lo) - a);
-    return (dl <= dr) ? lo - 1 : lo;
+    while (k > 0) {
+        const double dn = fabs(__ldg(ang + k - 1) - a);
+        if (dn <= dk) { --k; dk = dn; } else break;
+    }
+    return k;
 }
 
 // get_range (+ are_collinear), laser_models.py:230-280; v3 = (cos, sin)(beam_theta + pi/2) hoisted by the caller
@@ -620,7 +629,9 @@ __device__ __forceinline__ double get_range(double ox, double oy, double v3x, do
     return distance;
 }
 
-constexpr int POST_THREADS = 256;
+constexpr int POST_THREADS = 64;
+
+constexpr size_t post_smem_bytes(int A) { return sizeof(double) * (6 * A + 8 * A * A + (6 * A * A + 3 * A + 1) / 2 + 2 * A * A); }
 
 __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     const int env = blockIdx.x;
@@ -630,14 +641,19 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     const int tid = threadIdx.x;
     const int s_base = env * A;
 
-    __shared__ double s_pose[F110_MAX_AGENTS][3];        // own pose AFTER iTTC zeroing (ray-cast origin, :225)
-    __shared__ double s_pre[F110_MAX_AGENTS][3];         // Simulator.agent_poses: BEFORE iTTC zeroing (:587)
-    __shared__ double s_verts[F110_MAX_AGENTS * F110_MAX_AGENTS][8];  // opponent b seen by a, a's length/width
-    __shared__ int s_lo[F110_MAX_AGENTS * F110_MAX_AGENTS];
-    __shared__ int s_hi[F110_MAX_AGENTS * F110_MAX_AGENTS];
-    __shared__ int s_coll[F110_MAX_AGENTS];              // GJK flags
-    __shared__ int s_hit[F110_MAX_AGENTS];               // iTTC flags
-    __shared__ int s_lapdone[F110_MAX_AGENTS];
+    // dynamic shared memory sized by A (post_smem_bytes): 3 A + 3 A + 8 A^2 doubles, then 4 A^2 + 2 A^2 + 3 A ints
+    extern __shared__ double s_dyn[];
+    double (*s_pose)[3] = reinterpret_cast<double (*)[3]>(s_dyn);               // own pose AFTER iTTC zeroing (:225)
+    double (*s_pre)[3] = reinterpret_cast<double (*)[3]>(s_dyn + 3 * A);         // Simulator.agent_poses, BEFORE it (:587)
+    double (*s_verts)[8] = reinterpret_cast<double (*)[8]>(s_dyn + 6 * A);       // opponent b seen by a, a's length/width
+    int* s_ind = reinterpret_cast<int*>(s_dyn + 6 * A + 8 * A * A);              // nearest beam of each vertex
+    int* s_lo = s_ind + 4 * A * A;
+    int* s_hi = s_lo + A * A;
+    int* s_coll = s_hi + A * A;                                                  // GJK flags
+    int* s_hit = s_coll + A;                                                     // iTTC flags
+    int* s_lapdone = s_hit + A;
+    double* s_phi = s_dyn + 6 * A + 8 * A * A + (6 * A * A + 3 * A + 1) / 2;   // bearing of opponent b's centre in a's frame
+    double* s_alpha = s_phi + A * A;                                         // angular half-width of its bounding circle
 
     // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252
     if (tid < A) {
@@ -653,11 +669,33 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     }
     __syncthreads();
 
-    // ---- stage B: all-pairs GJK (check_collision :549-563) and per-(a, b) ray-cast windows (:206-227)
-    if (A > 1) {
-        for (int t = tid; t < A * A; t += POST_THREADS) {
-            const int a = t / A, b = t - a * A;
+    // ---- stage B: all-pairs GJK (check_collision :549-563) and the blocked-view window of every opponent b as seen
+    // from a (get_blocked_view_indices, laser_models.py:282-315): one thread per (a, b, vertex), one per GJK pair
+    const int nvert = A * A * 4;
+    for (int t = tid; t < nvert + A * A; t += POST_THREADS) {
+        if (t < nvert) {
+            const int a = t / (4 * A), b = (t >> 2) - a * A, k = t & 3;
             if (a == b) continue;
+            // vertex k of opponent b, a's own length/width (ray_cast_agents :223); order rl, rr, fr, fl
+            const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
+            double sb, cb;
+            sincos(s_pre[b][2], &sb, &cb);
+            const double hx = (k < 2) ? -L / 2 : L / 2;
+            const double hy = (k == 0 || k == 3) ? Wd / 2 : -Wd / 2;
+            const double vxw = cb * hx + (-sb) * hy + s_pre[b][0];
+            const double vyw = sb * hx + cb * hy + s_pre[b][1];
+            s_verts[a * A + b][2 * k] = vxw;
+            s_verts[a * A + b][2 * k + 1] = vyw;
+            double sn, cs;
+            sincos(s_pose[a][2], &sn, &cs);
+            const double vx = vxw - s_pose[a][0], vy = vyw - s_pose[a][1];
+            const double nrm = sqrt(vx * vx + vy * vy);
+            double ang = atan2(sn, cs) - atan2(vy / nrm, vx / nrm);
+            if (ang > F110_PI) ang = ang - 2 * F110_PI;
+            else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
+            s_ind[t] = nearest_beam(c.scan_angles, B, -ang);
+        } else {
+            const int p = t - nvert, a = p / A, b = p - a * A;
             if (a < b) {
                 double va[8], vb[8];
                 const double L = __ldg(c.sim_params + P_LENGTH), Wd = __ldg(c.sim_params + P_WIDTH);
@@ -665,30 +703,36 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
                 get_vertices(s_pre[b][0], s_pre[b][1], s_pre[b][2], L, Wd, vb);
                 if (gjk_collision(va, vb)) { s_coll[a] = 1; s_coll[b] = 1; }
             }
-            // opponent b as seen from a: a's own length/width (ray_cast_agents :223)
-            double* v = s_verts[t];
-            get_vertices(s_pre[b][0], s_pre[b][1], s_pre[b][2], __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH),
-                         __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH), v);
-            // get_blocked_view_indices, laser_models.py:282-315
-            double sn, cs;
-            sincos(s_pose[a][2], &sn, &cs);
-            const double ego_ang = atan2(sn, cs);
-            int lo = 0, hi = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double vx = v[2 * k] - s_pose[a][0], vy = v[2 * k + 1] - s_pose[a][1];
-                const double nrm = sqrt(vx * vx + vy * vy);
-                double ang = ego_ang - atan2(vy / nrm, vx / nrm);
-                if (ang > F110_PI) ang = ang - 2 * F110_PI;
-                else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
-                const int ind = nearest_beam(c.scan_angles, B, -ang);
-                if (k == 0) { lo = hi = ind; }
-                else { lo = ind < lo ? ind : lo; hi = ind > hi ? ind : hi; }
-            }
-            s_lo[t] = lo; s_hi[t] = hi;
         }
-        __syncthreads();
     }
+    __syncthreads();
+    for (int t = tid; t < A * A; t += POST_THREADS) {
+        const int* q = s_ind + 4 * t;
+        s_lo[t] = min(min(q[0], q[1]), min(q[2], q[3]));
+        s_hi[t] = max(max(q[0], q[1]), max(q[2], q[3]));
+        // The reference walks every beam of the window (all 1080 when the opponent is behind the car) although only
+        // beams whose LINE crosses the opponent can be lowered: a proper hit needs the ray to enter the car's bounding
+        // circle, and the collinear fallback of get_range (:270-274) needs the beam's line to contain an edge, forwards
+        // or backwards.  Beams further than alpha (+1e-6 rad) from both the bearing of the circle's centre and its
+        // opposite are skipped -- for them get_range returns inf on all four edges.
+        const int a = t / A, b = t - a * A;
+        if (a != b) {
+            const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
+            const double R = 0.5 * sqrt(L * L + Wd * Wd) * (1.0 + 1e-9) + 1e-9;
+            const double dx = s_pre[b][0] - s_pose[a][0], dy = s_pre[b][1] - s_pose[a][1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (!(dist > R * (1.0 + 1e-6))) {
+                s_phi[t] = 0.; s_alpha[t] = 4.0;     // overlapping (or NaN): every beam of the window
+            } else {
+                double phi = atan2(dy, dx) - s_pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
+                if (phi > F110_PI) phi -= 2 * F110_PI;
+                else if (phi < -F110_PI) phi += 2 * F110_PI;
+                s_phi[t] = phi;
+                s_alpha[t] = asin(R / dist) + 1e-6;
+            }
+        }
+    }
+    __syncthreads();
 
     // ---- stage C: finish zone / laps per agent, _check_done f110_env.py:320-348
     const double new_time = st.time[env] + c.timestep;   // :406 (read by every thread before thread 0 writes it back)
@@ -731,20 +775,34 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
         }
     }
 
-    // ---- stage D: opponent ray-cast + scan outputs + lidar part of the flat observation
+    // ---- stage D: opponent ray-cast (ray_cast_agents :206-227).  The lidar kernel already wrote every scan; only the
+    // beams inside some opponent's blocked-view window can get shorter, so only those are re-read (fp64 scratch
+    // copy), lowered and re-written.
     const float lm = c.lidar_max;
-    for (int idx = tid; idx < A * B; idx += POST_THREADS) {
-        const int a = idx / B;
-        const int i = idx - a * B;
-        const size_t g = (size_t)s_base * B + idx;
-        double range = sc.scan[g];
-        if (A > 1) {
+    for (int a = 0; a < A; ++a) {
+        int lo = B, hi = -1;
+        for (int b = 0; b < A; ++b) {
+            if (b == a) continue;
+            lo = min(lo, s_lo[a * A + b]);
+            hi = max(hi, s_hi[a * A + b]);
+        }
+        for (int i = lo + tid; i <= hi; i += POST_THREADS) {
+            const size_t g = (size_t)(s_base + a) * B + i;
+            const double range0 = sc.scan[g];
+            double range = range0;
             bool have_dir = false;
             double v3x = 0., v3y = 0.;
             for (int b = 0; b < A; ++b) {
                 if (b == a) continue;
                 const int t = a * A + b;
                 if (i < s_lo[t] || i > s_hi[t]) continue;
+                {
+                    double dl = __ldg(c.scan_angles + i) - s_phi[t];    // beam angles lie in (-pi, pi): one wrap suffices
+                    if (dl > F110_PI) dl -= 2 * F110_PI;
+                    else if (dl < -F110_PI) dl += 2 * F110_PI;
+                    dl = fabs(dl);                                       // in [0, pi]
+                    if (dl > s_alpha[t] && (F110_PI - dl) > s_alpha[t]) continue;
+                }
                 if (!have_dir) {
                     const double beam_theta = s_pose[a][2] + __ldg(c.scan_angles + i);
                     sincos(beam_theta + F110_PI / 2., &v3y, &v3x);
@@ -758,11 +816,11 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
                     if (rr < range) range = rr;
                 }
             }
-        }
-        if (io.scans_f64) io.scans_f64[g] = range;
-        if (io.scans_f32) io.scans_f32[g] = (float)range;
-        if (a == 0 && io.obs) {   // _pack_flat_obs f110_env.py:557-560 (e = 0 hard-coded)
-            io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
+            if (range < range0) {
+                if (io.scans_f64) io.scans_f64[g] = range;
+                if (io.scans_f32) io.scans_f32[g] = (float)range;
+                if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
+            }
         }
     }
     __syncthreads();
@@ -892,7 +950,7 @@ void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const
 
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     if (c.A == 1) post_single_kernel<<<(c.N + 127) / 128, 128, 0, s>>>(c, st, sc, io);
-    else post_kernel<<<c.N, POST_THREADS, 0, s>>>(c, st, sc, io);
+    else post_kernel<<<c.N, POST_THREADS, post_smem_bytes(c.A), s>>>(c, st, sc, io);
 }
 
 void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {
