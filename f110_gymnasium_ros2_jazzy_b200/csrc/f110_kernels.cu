@@ -594,7 +594,10 @@ __device__ __forceinline__ int nearest_beam(const double* __restrict__ ang, int 
     double g = (a - a0) / (a1 - a0) * (double)(B - 1);
     g = g < 0. ? 0. : (g > (double)(B - 1) ? (double)(B - 1) : g);
     int k = (int)(g + 0.5);
-    double dk = fabs(__ldg(ang + k) - a);
+    // the three candidates of a uniform table, loaded together
+    const int km = k > 0 ? k - 1 : 0, kp = k + 1 < B ? k + 1 : B - 1;
+    double dm = fabs(__ldg(ang + km) - a), dk = fabs(__ldg(ang + k) - a), dp = fabs(__ldg(ang + kp) - a);
+    if (dp < dk) { k = kp; dk = dp; } else if (dm <= dk && km != k) { k = km; dk = dm; }
     while (k + 1 < B) {
         const double dn = fabs(__ldg(ang + k + 1) - a);
         if (dn < dk) { ++k; dk = dn; } else break;
@@ -629,118 +632,169 @@ __device__ __forceinline__ double get_range(double ox, double oy, double v3x, do
     return distance;
 }
 
-constexpr int POST_THREADS = 64;
+constexpr int POST_THREADS = 128;
 
-constexpr size_t post_smem_bytes(int A) { return sizeof(double) * (6 * A + 8 * A * A + (6 * A * A + 3 * A + 1) / 2 + 2 * A * A); }
+// Shared memory of one env inside a post_kernel CTA (doubles first, then ints; sized by A).
+struct EnvSmem {
+    double (*pose)[3];   // [A]    own pose AFTER iTTC zeroing (ray-cast origin, base_classes.py:225)
+    double (*pre)[3];    // [A]    Simulator.agent_poses: BEFORE iTTC zeroing (:587)
+    double (*verts)[8];  // [A*A]  opponent b as seen by a: a's own length/width (:223)
+    int* ind;            // [4*A*A] nearest beam of each vertex
+    int* lo;             // [A*A]  blocked-view window (get_blocked_view_indices)
+    int* hi;
+    int* cone;           // [4*A*A] beam-index intervals [f0, f1], [b0, b1] of the forward / backward cones
+    int* coll;           // [A]    GJK flags, later GJK | iTTC
+    int* hit;            // [A]    iTTC flags
+    int* lapdone;        // [A]
+};
+__host__ __device__ constexpr int post_smem_doubles(int A) { return 6 * A + 8 * A * A + (10 * A * A + 3 * A + 1) / 2; }
+__device__ __forceinline__ EnvSmem env_smem(double* base, int A) {
+    EnvSmem e;
+    e.pose = reinterpret_cast<double (*)[3]>(base);
+    e.pre = reinterpret_cast<double (*)[3]>(base + 3 * A);
+    e.verts = reinterpret_cast<double (*)[8]>(base + 6 * A);
+    e.ind = reinterpret_cast<int*>(base + 6 * A + 8 * A * A);
+    e.lo = e.ind + 4 * A * A;
+    e.hi = e.lo + A * A;
+    e.cone = e.hi + A * A;
+    e.coll = e.cone + 4 * A * A;
+    e.hit = e.coll + A;
+    e.lapdone = e.hit + A;
+    return e;
+}
+// envs per CTA: enough of them that the 5 A^2 scalar work items of stage B fill the CTA's lanes
+__host__ __device__ constexpr int post_envs_per_cta(int A) {
+    return (POST_THREADS / (5 * A * A)) < 1 ? 1 : ((POST_THREADS / (5 * A * A)) > 16 ? 16 : (POST_THREADS / (5 * A * A)));
+}
 
 __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
-    const int env = blockIdx.x;
-    if (env == 0 && threadIdx.x == 0) latch_launch_order(sc);
-    if (io.active_mask && !io.active_mask[env]) return;
     const int A = c.A, B = c.B;
     const int tid = threadIdx.x;
-    const int s_base = env * A;
-
-    // dynamic shared memory sized by A (post_smem_bytes): 3 A + 3 A + 8 A^2 doubles, then 4 A^2 + 2 A^2 + 3 A ints
+    const int epc = post_envs_per_cta(A);
+    const int env0 = blockIdx.x * epc;
+    if (blockIdx.x == 0 && tid == 0) latch_launch_order(sc);
     extern __shared__ double s_dyn[];
-    double (*s_pose)[3] = reinterpret_cast<double (*)[3]>(s_dyn);               // own pose AFTER iTTC zeroing (:225)
-    double (*s_pre)[3] = reinterpret_cast<double (*)[3]>(s_dyn + 3 * A);         // Simulator.agent_poses, BEFORE it (:587)
-    double (*s_verts)[8] = reinterpret_cast<double (*)[8]>(s_dyn + 6 * A);       // opponent b seen by a, a's length/width
-    int* s_ind = reinterpret_cast<int*>(s_dyn + 6 * A + 8 * A * A);              // nearest beam of each vertex
-    int* s_lo = s_ind + 4 * A * A;
-    int* s_hi = s_lo + A * A;
-    int* s_coll = s_hi + A * A;                                                  // GJK flags
-    int* s_hit = s_coll + A;                                                     // iTTC flags
-    int* s_lapdone = s_hit + A;
-    double* s_phi = s_dyn + 6 * A + 8 * A * A + (6 * A * A + 3 * A + 1) / 2;   // bearing of opponent b's centre in a's frame
-    double* s_alpha = s_phi + A * A;                                         // angular half-width of its bounding circle
+    const int stride = post_smem_doubles(A);
+    __shared__ int s_active[16];
+    if (tid < epc) {
+        const int env = env0 + tid;
+        s_active[tid] = env < c.N && !(io.active_mask && !io.active_mask[env]);
+    }
+    __syncthreads();
 
-    // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252
-    if (tid < A) {
-        const int s = s_base + tid;
+    // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252.  One thread per (env, agent).
+    for (int t = tid; t < epc * A; t += POST_THREADS) {
+        const int le = t / A, a = t - le * A;
+        if (!s_active[le]) continue;
+        const EnvSmem e = env_smem(s_dyn + le * stride, A);
+        const int s = (env0 + le) * A + a;
         const int hit = sc.ttc_hit[s];
         const double px = st.x[0][s], py = st.x[1][s];
         const double yaw_pre = sc.pre_yaw[s];
         if (hit) { st.x[3][s] = 0.; st.x[4][s] = 0.; st.x[5][s] = 0.; st.x[6][s] = 0.; }
-        s_pose[tid][0] = px; s_pose[tid][1] = py; s_pose[tid][2] = hit ? 0. : yaw_pre;
-        s_pre[tid][0] = px; s_pre[tid][1] = py; s_pre[tid][2] = yaw_pre;
-        s_hit[tid] = hit;
-        s_coll[tid] = 0;
+        e.pose[a][0] = px; e.pose[a][1] = py; e.pose[a][2] = hit ? 0. : yaw_pre;
+        e.pre[a][0] = px; e.pre[a][1] = py; e.pre[a][2] = yaw_pre;
+        e.hit[a] = hit;
+        e.coll[a] = 0;
     }
     __syncthreads();
 
     // ---- stage B: all-pairs GJK (check_collision :549-563) and the blocked-view window of every opponent b as seen
-    // from a (get_blocked_view_indices, laser_models.py:282-315): one thread per (a, b, vertex), one per GJK pair
-    const int nvert = A * A * 4;
-    for (int t = tid; t < nvert + A * A; t += POST_THREADS) {
-        if (t < nvert) {
-            const int a = t / (4 * A), b = (t >> 2) - a * A, k = t & 3;
+    // from a (get_blocked_view_indices, laser_models.py:282-315): one thread per (env, a, b, vertex) and per GJK pair
+    const int nvert = A * A * 4, nitem = nvert + A * A;
+    for (int t = tid; t < epc * nitem; t += POST_THREADS) {
+        const int le = t / nitem, u = t - le * nitem;
+        if (!s_active[le]) continue;
+        const EnvSmem e = env_smem(s_dyn + le * stride, A);
+        if (u < nvert) {
+            const int a = u / (4 * A), b = (u >> 2) - a * A, k = u & 3;
             if (a == b) continue;
             // vertex k of opponent b, a's own length/width (ray_cast_agents :223); order rl, rr, fr, fl
             const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
             double sb, cb;
-            sincos(s_pre[b][2], &sb, &cb);
+            sincos(e.pre[b][2], &sb, &cb);
             const double hx = (k < 2) ? -L / 2 : L / 2;
             const double hy = (k == 0 || k == 3) ? Wd / 2 : -Wd / 2;
-            const double vxw = cb * hx + (-sb) * hy + s_pre[b][0];
-            const double vyw = sb * hx + cb * hy + s_pre[b][1];
-            s_verts[a * A + b][2 * k] = vxw;
-            s_verts[a * A + b][2 * k + 1] = vyw;
-            double sn, cs;
-            sincos(s_pose[a][2], &sn, &cs);
-            const double vx = vxw - s_pose[a][0], vy = vyw - s_pose[a][1];
-            const double nrm = sqrt(vx * vx + vy * vy);
-            double ang = atan2(sn, cs) - atan2(vy / nrm, vx / nrm);
+            const double vxw = cb * hx + (-sb) * hy + e.pre[b][0];
+            const double vyw = sb * hx + cb * hy + e.pre[b][1];
+            e.verts[a * A + b][2 * k] = vxw;
+            e.verts[a * A + b][2 * k + 1] = vyw;
+            // arctan2(sin(yaw), cos(yaw)) == yaw for the wrapped yaw and arctan2(v/|v|) == arctan2(v), each to an ulp; the
+            // angle only selects the nearest beam, so the shorter dependent chain cannot change a window except at an
+            // exact tie between two beams
+            const double vx = vxw - e.pose[a][0], vy = vyw - e.pose[a][1];
+            double ang = e.pose[a][2] - atan2(vy, vx);
+            if (vx == 0. && vy == 0.) ang = nan("");   // the reference divides by the zero norm -> NaN -> argmin 0
             if (ang > F110_PI) ang = ang - 2 * F110_PI;
             else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
-            s_ind[t] = nearest_beam(c.scan_angles, B, -ang);
+            e.ind[u] = nearest_beam(c.scan_angles, B, -ang);
         } else {
-            const int p = t - nvert, a = p / A, b = p - a * A;
+            const int p = u - nvert, a = p / A, b = p - a * A;
             if (a < b) {
                 double va[8], vb[8];
                 const double L = __ldg(c.sim_params + P_LENGTH), Wd = __ldg(c.sim_params + P_WIDTH);
-                get_vertices(s_pre[a][0], s_pre[a][1], s_pre[a][2], L, Wd, va);
-                get_vertices(s_pre[b][0], s_pre[b][1], s_pre[b][2], L, Wd, vb);
-                if (gjk_collision(va, vb)) { s_coll[a] = 1; s_coll[b] = 1; }
+                get_vertices(e.pre[a][0], e.pre[a][1], e.pre[a][2], L, Wd, va);
+                get_vertices(e.pre[b][0], e.pre[b][1], e.pre[b][2], L, Wd, vb);
+                if (gjk_collision(va, vb)) { e.coll[a] = 1; e.coll[b] = 1; }
             }
         }
     }
     __syncthreads();
-    for (int t = tid; t < A * A; t += POST_THREADS) {
-        const int* q = s_ind + 4 * t;
-        s_lo[t] = min(min(q[0], q[1]), min(q[2], q[3]));
-        s_hi[t] = max(max(q[0], q[1]), max(q[2], q[3]));
+    for (int t = tid; t < epc * A * A; t += POST_THREADS) {
+        const int le = t / (A * A), u = t - le * A * A;
+        if (!s_active[le]) continue;
+        const EnvSmem e = env_smem(s_dyn + le * stride, A);
+        const int* q = e.ind + 4 * u;
+        const int a = u / A, b = u - a * A;
+        if (a == b) { e.lo[u] = B; e.hi[u] = -1; e.cone[4 * u] = B; e.cone[4 * u + 1] = -1; e.cone[4 * u + 2] = B; e.cone[4 * u + 3] = -1; continue; }
+        e.lo[u] = min(min(q[0], q[1]), min(q[2], q[3]));
+        e.hi[u] = max(max(q[0], q[1]), max(q[2], q[3]));
         // The reference walks every beam of the window (all 1080 when the opponent is behind the car) although only
         // beams whose LINE crosses the opponent can be lowered: a proper hit needs the ray to enter the car's bounding
         // circle, and the collinear fallback of get_range (:270-274) needs the beam's line to contain an edge, forwards
         // or backwards.  Beams further than alpha (+1e-6 rad) from both the bearing of the circle's centre and its
-        // opposite are skipped -- for them get_range returns inf on all four edges.
-        const int a = t / A, b = t - a * A;
-        if (a != b) {
-            const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
-            const double R = 0.5 * sqrt(L * L + Wd * Wd) * (1.0 + 1e-9) + 1e-9;
-            const double dx = s_pre[b][0] - s_pose[a][0], dy = s_pre[b][1] - s_pose[a][1];
-            const double dist = sqrt(dx * dx + dy * dy);
-            if (!(dist > R * (1.0 + 1e-6))) {
-                s_phi[t] = 0.; s_alpha[t] = 4.0;     // overlapping (or NaN): every beam of the window
-            } else {
-                double phi = atan2(dy, dx) - s_pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
-                if (phi > F110_PI) phi -= 2 * F110_PI;
-                else if (phi < -F110_PI) phi += 2 * F110_PI;
-                s_phi[t] = phi;
-                s_alpha[t] = asin(R / dist) + 1e-6;
+        // opposite are never visited -- for them get_range returns inf on all four edges.
+        const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
+        const double R = 0.5 * sqrt(L * L + Wd * Wd) * (1.0 + 1e-9) + 1e-9;
+        const double dx = e.pre[b][0] - e.pose[a][0], dy = e.pre[b][1] - e.pose[a][1];
+        const double dist = sqrt(dx * dx + dy * dy);
+        // cone -> beam-index intervals (supersets by one beam each side), clipped to the reference window
+        int f0 = e.lo[u], f1 = e.hi[u], b0 = B, b1 = -1;
+        const double alpha = asin(R / dist) + 1e-6;
+        if (dist > R * (1.0 + 1e-6) && alpha < 0.75) {
+            // beam angles lie inside (-pi + 0.75, pi - 0.75) (fov <= 4.7 rad): a cone of half-width < 0.75 around a
+            // bearing in [-pi, pi] can only meet them un-wrapped
+            double phi = atan2(dy, dx) - e.pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
+            if (phi > F110_PI) phi -= 2 * F110_PI;
+            else if (phi < -F110_PI) phi += 2 * F110_PI;
+            const double back = phi > 0. ? phi - F110_PI : phi + F110_PI;
+            const double amin = __ldg(c.scan_angles), amax = __ldg(c.scan_angles + B - 1);
+            if (phi + alpha < amin || phi - alpha > amax) { f0 = B; f1 = -1; }
+            else {
+                f0 = max(f0, nearest_beam(c.scan_angles, B, phi - alpha) - 1);
+                f1 = min(f1, nearest_beam(c.scan_angles, B, phi + alpha) + 1);
             }
-        }
+            if (!(back + alpha < amin || back - alpha > amax)) {
+                b0 = max(e.lo[u], nearest_beam(c.scan_angles, B, back - alpha) - 1);
+                b1 = min(e.hi[u], nearest_beam(c.scan_angles, B, back + alpha) + 1);
+                if (b0 <= f1 && f0 <= b1) { f0 = min(f0, b0); f1 = max(f1, b1); b0 = B; b1 = -1; }   // merge overlap
+            }
+        }   // else: overlapping cars, NaN, or a cone too wide to reason about -> the whole reference window
+        e.cone[4 * u] = f0; e.cone[4 * u + 1] = f1; e.cone[4 * u + 2] = b0; e.cone[4 * u + 3] = b1;
     }
     __syncthreads();
 
     // ---- stage C: finish zone / laps per agent, _check_done f110_env.py:320-348
-    const double new_time = st.time[env] + c.timestep;   // :406 (read by every thread before thread 0 writes it back)
-    if (tid < A) {
-        const int s = s_base + tid;
-        const int col = (s_coll[tid] | s_hit[tid]) ? 1 : 0;
-        const double dxp = s_pose[tid][0] - st.start_x[s];
-        const double dyp = s_pose[tid][1] - st.start_y[s];
+    for (int t = tid; t < epc * A; t += POST_THREADS) {
+        const int le = t / A, a = t - le * A;
+        if (!s_active[le]) continue;
+        const EnvSmem e = env_smem(s_dyn + le * stride, A);
+        const int env = env0 + le;
+        const int s = env * A + a;
+        const double new_time = st.time[env] + c.timestep;   // :406 (written back in stage E, after the barrier)
+        const int col = (e.coll[a] | e.hit[a]) ? 1 : 0;
+        const double dxp = e.pose[a][0] - st.start_x[s];
+        const double dyp = e.pose[a][1] - st.start_y[s];
         const double rc = st.rot_c[env], rs = st.rot_s[env];
         // start_rot = [[cos(-t), -sin(-t)], [sin(-t), cos(-t)]]
         const double lx = rc * dxp + (-rs) * dyp;
@@ -761,17 +815,15 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
         double lapt = st.lap_times[s];
         if (tog < 4) { lapt = new_time; st.lap_times[s] = lapt; }
         st.collisions[s] = (uint8_t)col;
-        s_lapdone[tid] = tog >= 4;
-        s_coll[tid] = col;
+        e.lapdone[a] = tog >= 4;
         if (io.collisions) io.collisions[s] = (uint8_t)col;
         if (io.toggles) io.toggles[s] = tog;
         if (io.lap_times) io.lap_times[s] = lapt;
         if (io.lap_counts) io.lap_counts[s] = lapc;
         if (io.state) {
             double* o = io.state + (size_t)s * 7;
-            o[0] = s_pose[tid][0]; o[1] = s_pose[tid][1]; o[2] = st.x[2][s];
-            if (s_hit[tid]) { o[3] = 0.; o[4] = 0.; o[5] = 0.; o[6] = 0.; }
-            else { o[3] = st.x[3][s]; o[4] = s_pose[tid][2]; o[5] = st.x[5][s]; o[6] = st.x[6][s]; }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) o[k] = st.x[k][s];   // this thread wrote the zeroed entries itself in stage A
         }
     }
 
@@ -779,80 +831,70 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     // beams inside some opponent's blocked-view window can get shorter, so only those are re-read (fp64 scratch
     // copy), lowered and re-written.
     const float lm = c.lidar_max;
-    for (int a = 0; a < A; ++a) {
-        int lo = B, hi = -1;
-        for (int b = 0; b < A; ++b) {
-            if (b == a) continue;
-            lo = min(lo, s_lo[a * A + b]);
-            hi = max(hi, s_hi[a * A + b]);
-        }
-        for (int i = lo + tid; i <= hi; i += POST_THREADS) {
-            const size_t g = (size_t)(s_base + a) * B + i;
-            const double range0 = sc.scan[g];
-            double range = range0;
-            bool have_dir = false;
-            double v3x = 0., v3y = 0.;
-            for (int b = 0; b < A; ++b) {
-                if (b == a) continue;
-                const int t = a * A + b;
-                if (i < s_lo[t] || i > s_hi[t]) continue;
-                {
-                    double dl = __ldg(c.scan_angles + i) - s_phi[t];    // beam angles lie in (-pi, pi): one wrap suffices
-                    if (dl > F110_PI) dl -= 2 * F110_PI;
-                    else if (dl < -F110_PI) dl += 2 * F110_PI;
-                    dl = fabs(dl);                                       // in [0, pi]
-                    if (dl > s_alpha[t] && (F110_PI - dl) > s_alpha[t]) continue;
-                }
-                if (!have_dir) {
-                    const double beam_theta = s_pose[a][2] + __ldg(c.scan_angles + i);
-                    sincos(beam_theta + F110_PI / 2., &v3y, &v3x);
-                    have_dir = true;
-                }
-                const double* v = s_verts[t];
+    for (int q = 0; q < epc * A * A; ++q) {
+        const int le = q / (A * A), u = q - le * A * A;
+        if (!s_active[le]) continue;
+        const EnvSmem e = env_smem(s_dyn + le * stride, A);
+        const int a = u / A;
+        const int env = env0 + le;
+        const double* v = e.verts[u];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i0 = e.cone[4 * u + 2 * half], i1 = e.cone[4 * u + 2 * half + 1];
+            // beam i always belongs to thread i % POST_THREADS, so successive opponents of the same car lower a beam
+            // through the same thread, in the reference's order, via the scratch copy
+            for (int i = (i0 & ~(POST_THREADS - 1)) + tid; i <= i1; i += POST_THREADS) {
+                if (i < i0) continue;
+                const size_t g = (size_t)(env * A + a) * B + i;
+                const double range0 = sc.scan[g];
+                double range = range0;
+                double v3x, v3y;
+                sincos(e.pose[a][2] + __ldg(c.scan_angles + i) + F110_PI / 2., &v3y, &v3x);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int j2 = (j + 1) & 3;
-                    const double rr = get_range(s_pose[a][0], s_pose[a][1], v3x, v3y, v[2 * j], v[2 * j + 1], v[2 * j2], v[2 * j2 + 1]);
+                    const double rr = get_range(e.pose[a][0], e.pose[a][1], v3x, v3y, v[2 * j], v[2 * j + 1], v[2 * j2], v[2 * j2 + 1]);
                     if (rr < range) range = rr;
                 }
-            }
-            if (range < range0) {
-                if (io.scans_f64) io.scans_f64[g] = range;
-                if (io.scans_f32) io.scans_f32[g] = (float)range;
-                if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
+                if (range < range0) {
+                    sc.scan[g] = range;
+                    if (io.scans_f64) io.scans_f64[g] = range;
+                    if (io.scans_f32) io.scans_f32[g] = (float)range;
+                    if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
+                }
             }
         }
     }
     __syncthreads();
 
-    // ---- stage E: done, reward, time, pose part of the observation, episode statistics
-    if (tid == 0) {
+    // ---- stage E: done, reward, time, pose part of the observation, episode statistics.  One thread per env.
+    if (tid < epc && s_active[tid]) {
+        const EnvSmem e = env_smem(s_dyn + tid * stride, A);
+        const int env = env0 + tid;
+        const double new_time = st.time[env] + c.timestep;
         bool all_laps = true;
-        for (int a = 0; a < A; ++a) all_laps = all_laps && s_lapdone[a];
-        const bool done = (s_coll[c.ego] != 0) || all_laps;   // f110_env.py:350
+        for (int a = 0; a < A; ++a) all_laps = all_laps && e.lapdone[a];
+        const bool ego_col = (e.coll[c.ego] | e.hit[c.ego]) != 0;
+        const bool done = ego_col || all_laps;   // f110_env.py:350
         st.time[env] = new_time;
         if (io.time) io.time[env] = new_time;
         if (io.reward) io.reward[env] = (float)c.timestep;
         if (io.terminated) io.terminated[env] = done ? 1 : 0;
-        if (io.obs) {   // f110_env.py:563-579: slots for agents 0 and 1 (zeros when A == 1)
+        if (io.obs) {   // f110_env.py:563-579: slots for agents 0 and 1
             float* q = io.obs + (size_t)env * (B + 8) + B;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                if (k < A) {
-                    q[4 * k] = (float)s_pose[k][0];
-                    q[4 * k + 1] = (float)s_pose[k][1];
-                    q[4 * k + 2] = (float)wrap_angle(s_pose[k][2]);
-                    q[4 * k + 3] = s_coll[k] ? 1.0f : 0.0f;
-                } else {
-                    q[4 * k] = q[4 * k + 1] = q[4 * k + 2] = q[4 * k + 3] = 0.0f;
-                }
+                q[4 * k] = (float)e.pose[k][0];
+                q[4 * k + 1] = (float)e.pose[k][1];
+                q[4 * k + 2] = (float)wrap_angle(e.pose[k][2]);
+                q[4 * k + 3] = (e.coll[k] | e.hit[k]) ? 1.0f : 0.0f;
             }
         }
         if (done) {
             atomicAdd(sc.stats + F110_STAT_EPISODES, 1.0);
             atomicAdd(sc.stats + F110_STAT_EPISODE_STEPS, (double)st.step_count[env] + 1.0);
             atomicAdd(sc.stats + F110_STAT_EPISODE_TIME, new_time);
-            if (s_coll[c.ego]) atomicAdd(sc.stats + F110_STAT_EGO_COLLISIONS, 1.0);
+            if (ego_col) atomicAdd(sc.stats + F110_STAT_EGO_COLLISIONS, 1.0);
             if (all_laps) atomicAdd(sc.stats + F110_STAT_LAPS_DONE, 1.0);
         }
     }
@@ -950,7 +992,10 @@ void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const
 
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     if (c.A == 1) post_single_kernel<<<(c.N + 127) / 128, 128, 0, s>>>(c, st, sc, io);
-    else post_kernel<<<c.N, POST_THREADS, post_smem_bytes(c.A), s>>>(c, st, sc, io);
+    else {
+        const int epc = post_envs_per_cta(c.A);
+        post_kernel<<<(c.N + epc - 1) / epc, POST_THREADS, sizeof(double) * post_smem_doubles(c.A) * epc, s>>>(c, st, sc, io);
+    }
 }
 
 void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {
