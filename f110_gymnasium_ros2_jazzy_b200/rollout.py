@@ -1,0 +1,89 @@
+"""Device-resident rollout loop (SURVEY 8f row 1 / BASELINE config 5).
+
+The reference's training loop (rl_training/train_ddpg.py:160-202) does, per step and on the host:
+ego action from the actor, opponent action ``gap_follow_action(info["scans"][1])``, ``np.stack``, ``env.step``.
+Here the same loop shape runs with every tensor on the GPU: the actor is a torch module evaluated on the observation
+tensor the step kernels wrote (zero-copy), the opponent is the ``f110_gap_follow`` kernel reading the opponent's scan
+in place and writing its action slot in place, and the step consumes the action tensor in place.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def gap_follow_actions(scans_f32, actions, agent_idx=1, angle_min=-np.pi / 2, angle_increment=np.pi / 1080,
+                       max_distance=3.0, window_size=5, bubble_radius=30, threshold=0.5):
+    """Batched gap_follow_action (gap_follow.py:43-58): for every env, agent ``agent_idx``'s scan -> its action slot.
+
+    scans_f32: CUDA float32 [N, A, B] (F110VecEnv output 'scans_f32'); actions: CUDA float32 [N, A, 2], written in place.
+    """
+    if not (scans_f32.is_cuda and actions.is_cuda and scans_f32.dtype == torch.float32 and actions.dtype == torch.float32):
+        raise ValueError("gap_follow_actions needs CUDA float32 tensors")
+    if not (scans_f32.is_contiguous() and actions.is_contiguous()):
+        raise ValueError("gap_follow_actions needs contiguous tensors")
+    N, A, B = scans_f32.shape
+    lib = _lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream(scans_f32.device).cuda_stream)
+    _lib.check(lib.f110_gap_follow(C.c_void_p(scans_f32.data_ptr() + 4 * agent_idx * B), N, A * B, B,
+                                   C.c_void_p(actions.data_ptr() + 4 * 2 * agent_idx), 2 * A, angle_min, angle_increment,
+                                   max_distance, window_size, bubble_radius, threshold, stream))
+    return actions
+
+
+class Actor(torch.nn.Module):
+    """The reference's DDPG actor architecture (rl_training/DDPG/agent.py:25-62): obs -> 128 -> 128 -> act, ReLU,
+    tanh scaled to the action bounds.  The learner itself is out of scope; this is what a rollout evaluates."""
+
+    def __init__(self, obs_dim, act_dim, action_low, action_high):
+        super().__init__()
+        self.fc1 = torch.nn.Linear(obs_dim, 128)
+        self.fc2 = torch.nn.Linear(128, 128)
+        self.fc3 = torch.nn.Linear(128, act_dim)
+        self.register_buffer("action_low", torch.tensor(action_low, dtype=torch.float32))
+        self.register_buffer("action_high", torch.tensor(action_high, dtype=torch.float32))
+        torch.nn.init.kaiming_uniform_(self.fc1.weight, nonlinearity="relu")
+        torch.nn.init.kaiming_uniform_(self.fc2.weight, nonlinearity="relu")
+        torch.nn.init.uniform_(self.fc3.weight, -3e-3, 3e-3)
+        for b in (self.fc1.bias, self.fc2.bias, self.fc3.bias):
+            torch.nn.init.zeros_(b)
+
+    def forward(self, obs):
+        x = torch.relu(self.fc1(obs))
+        x = torch.relu(self.fc2(x))
+        t = torch.tanh(self.fc3(x))
+        return 0.5 * (self.action_high - self.action_low) * t + 0.5 * (self.action_high + self.action_low)
+
+
+class DeviceRollout(object):
+    """ego = policy(obs), opponent = gap-follow on its own scan, env.step -- no host round trip per step.
+
+    ``env`` is an F110VecEnv with num_agents == 2 and 'scans_f32' among its outputs; ``policy`` maps the observation
+    tensor [N, B+8] to ego actions [N, 2] (e.g. Actor).  ``opponent`` may be 'gap_follow' or a constant (steer, speed).
+    """
+
+    def __init__(self, env, policy, opponent='gap_follow'):
+        if env.num_agents != 2:
+            raise ValueError("DeviceRollout mirrors the reference's two-car loop (ego + opponent)")
+        if opponent == 'gap_follow' and 'scans_f32' not in env.backend.out:
+            raise ValueError("the gap-follow opponent needs the env's 'scans_f32' output")
+        self.env, self.policy, self.opponent = env, policy, opponent
+        self.actions = torch.zeros((env.num_envs, 2, 2), dtype=torch.float32, device=env.device)
+        if opponent != 'gap_follow':
+            self.actions[:, 1, 0] = float(opponent[0])
+            self.actions[:, 1, 1] = float(opponent[1])
+        self.obs = None
+
+    def reset(self, poses):
+        self.obs, _ = self.env.reset(poses)
+        return self.obs
+
+    @torch.no_grad()
+    def step(self):
+        self.actions[:, 0, :] = self.policy(self.obs)
+        if self.opponent == 'gap_follow':
+            gap_follow_actions(self.env.backend.out['scans_f32'], self.actions, agent_idx=1)
+        self.obs, reward, terminated, truncated, info = self.env.step(self.actions)
+        return self.obs, reward, terminated, truncated, info

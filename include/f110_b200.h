@@ -177,6 +177,15 @@ int f110_get_kernel_timing(F110Sim* sim, double* ms3, int64_t* steps);
 /* Launch bookkeeping for bench.py: kernels launched by this handle since creation. */
 int64_t f110_kernel_launches(const F110Sim* sim);
 
+/* ---- consumers around the env, on the device ----
+ * gap_follow_action (rl_training/utils/gap_follow.py:43-58), the rule-based opponent train_ddpg.py:168 drives from
+ * info["scans"][1]: for scan k (DEVICE float[num_beams] at scans + k*scan_stride) writes (steer, speed) as two floats
+ * at actions + k*action_stride.  Defaults of the reference: angle_min = -pi/2, angle_increment = pi/1080,
+ * max_distance 3.0, window_size 5, bubble_radius 30, threshold 0.5.  Strides are in elements. */
+int f110_gap_follow(const float* scans, int64_t num_scans, int64_t scan_stride, int32_t num_beams,
+                    float* actions, int64_t action_stride, double angle_min, double angle_increment,
+                    float max_distance, int32_t window_size, int32_t bubble_radius, float threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -859,3 +859,54 @@ int f110o_sim_reset(F110Oracle* o, const double* poses /*[N][A][3]*/, int num_po
 }
 
 long f110o_last_lookups(F110Oracle* o) { return o->lookups; }
+
+/* ------------------------------------------------------------------ rl_training/utils/gap_follow.py
+ * (the rule-based opponent of train_ddpg.py:168).  Paths relative to /root/reference/.
+ * preprocess_lidar :3-12, create_bubble :14-19, find_max_gap :21-38, find_best_point :40-41,
+ * gap_follow_action :43-58.  scan is float32 (info["scans"][1]); numpy's mean of a float32 slice
+ * shorter than 8 accumulates sequentially in float32 and divides by the count in float32. */
+void f110o_gap_follow(const float* scan, int n, double angle_min, double angle_increment,
+                      float max_distance, int window_size, int bubble_radius, float threshold,
+                      double* steer_out, double* speed_out, int* best_out, float* proc_out /* [n] or NULL */) {
+    float* proc = (float*)malloc(sizeof(float) * n);
+    int half = window_size / 2;
+    for (int i = 0; i < n; ++i) {
+        int s = i - half < 0 ? 0 : i - half;
+        int e = i + half > n - 1 ? n - 1 : i + half;
+        float acc = 0.f;
+        for (int k = s; k <= e; ++k) {
+            float v = scan[k];
+            if (v < 0.f) v = 0.f;
+            if (v > max_distance) v = max_distance;
+            acc += v;
+        }
+        proc[i] = acc / (float)(e - s + 1);
+    }
+    if (proc_out) memcpy(proc_out, proc, sizeof(float) * n);
+    int closest = 0;
+    for (int i = 1; i < n; ++i) if (proc[i] < proc[closest]) closest = i;
+    {
+        int s = closest - bubble_radius < 0 ? 0 : closest - bubble_radius;
+        int e = closest + bubble_radius > n - 1 ? n - 1 : closest + bubble_radius;
+        for (int i = s; i <= e; ++i) proc[i] = 0.f;
+    }
+    int best_s = 0, best_e = n - 1, best_len = -1, start = -1;
+    for (int i = 0; i < n; ++i) {
+        int val = proc[i] > threshold;
+        if (val && start < 0) start = i;
+        else if (!val && start >= 0) {
+            if (i - 1 - start > best_len) { best_len = i - 1 - start; best_s = start; best_e = i - 1; }
+            start = -1;
+        }
+    }
+    if (start >= 0 && n - 1 - start > best_len) { best_len = n - 1 - start; best_s = start; best_e = n - 1; }
+    int best = (best_s + best_e) / 2;
+    double steering = angle_min + best * angle_increment;
+    double speed;
+    const double d10 = 10 * (PI / 180.0), d20 = 20 * (PI / 180.0);   /* np.radians */
+    if (fabs(steering) < d10) speed = 2.5;
+    else if (fabs(steering) < d20) speed = 2;
+    else speed = 1.5;
+    *steer_out = steering; *speed_out = speed; *best_out = best;
+    free(proc);
+}

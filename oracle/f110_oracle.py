@@ -65,6 +65,8 @@ def lib():
         L.f110o_collision.argtypes = [vp, vp]
         L.f110o_collision.restype = C.c_int
         L.f110o_collision_multiple.argtypes = [vp, C.c_int, vp, vp]
+        L.f110o_gap_follow.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, C.c_float,
+                                       dp, dp, C.POINTER(C.c_int), vp]
         _LIB = L
     return _LIB
 
@@ -270,3 +272,15 @@ class Oracle(object):
         c, i = np.empty(n), np.empty(n)
         self.L.f110o_collision_multiple(_p(vertices), n, _p(c), _p(i))
         return c, i
+
+
+def gap_follow_action(scan, angle_min=-np.pi / 2, angle_increment=np.pi / 1080, want_proc=False):
+    """rl_training/utils/gap_follow.py:43-58 restated (oracle): float32 scan -> (steer, speed) as float64."""
+    L = lib()
+    scan = np.ascontiguousarray(scan, np.float32)
+    st, sp, best = C.c_double(), C.c_double(), C.c_int()
+    proc = np.empty(scan.shape[0], np.float32) if want_proc else None
+    L.f110o_gap_follow(_p(scan), scan.shape[0], angle_min, angle_increment, 3.0, 5, 30, 0.5, C.byref(st), C.byref(sp),
+                       C.byref(best), _p(proc))
+    out = np.array([st.value, sp.value])
+    return (out, proc) if want_proc else out

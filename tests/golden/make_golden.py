@@ -184,5 +184,35 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
 
 
+def make_gap_follow_golden():
+    """rl_training/utils/gap_follow.py:43-58 on recorded + synthetic scans -> tests/golden/gap_follow.npz"""
+    sys.path.insert(0, os.path.join(REF_ROOT, 'rl_training'))
+    from utils.gap_follow import gap_follow_action, preprocess_lidar
+    rng = np.random.default_rng(5)
+    scans = []
+    for f in ('rollout_c2_shanghai', 'rollout_headon_open', 'rollout_corridor', 'rollout_circles_open'):
+        g = np.load(os.path.join(HERE, f + '.npz'))
+        scans.append(g['scans'].reshape(-1, 1080).astype(np.float32))
+    scans = np.concatenate(scans)
+    extra = [np.full(1080, 0.2, np.float32), np.full(1080, 5.0, np.float32), np.zeros(1080, np.float32),
+             np.linspace(0, 6, 1080).astype(np.float32), np.linspace(6, 0, 1080).astype(np.float32)]
+    for _ in range(40):
+        s = rng.uniform(0.0, 4.0, 1080).astype(np.float32)
+        s[rng.integers(0, 1080, 30)] = rng.uniform(0, 0.4, 30).astype(np.float32)   # narrow obstacles
+        k = rng.integers(0, 900); s[k:k + rng.integers(5, 180)] = 0.3                 # a wall segment
+        extra.append(s)
+    nanscan = rng.uniform(0.6, 3.0, 1080).astype(np.float32); nanscan[100] = 30.0
+    extra.append(nanscan)
+    scans = np.concatenate([scans, np.stack(extra)])
+    acts = np.stack([gap_follow_action(s.copy()) for s in scans])
+    proc = np.stack([preprocess_lidar(s) for s in scans[:8]])
+    np.savez_compressed(os.path.join(HERE, 'gap_follow.npz'), scans=scans, actions=acts, proc=proc)
+    print('gap_follow.npz', scans.shape, acts.dtype, proc.dtype)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'gap_follow':
+        make_gap_follow_golden()     # only the consumer-side fixture
+    else:
+        main()
+        make_gap_follow_golden()

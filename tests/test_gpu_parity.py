@@ -363,3 +363,52 @@ def test_step_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     for k in a.out:
         assert torch.equal(a.out[k], b.out[k]), k
+
+
+def test_gap_follow_kernel_bit_exact():
+    """f110_gap_follow against the reference's gap_follow_action (golden) and the oracle, through strided views."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import gap_follow_actions
+    from oracle.f110_oracle import gap_follow_action
+    g = H.load('gap_follow')
+    scans = g['scans']
+    N = len(scans)
+    rng = np.random.default_rng(9)
+    more = rng.uniform(0, 5, size=(300, 1080)).astype(np.float32)
+    more[:, 200:260] *= rng.uniform(0, 0.2, size=(300, 1)).astype(np.float32)
+    allscans = np.concatenate([scans, more])
+    M = len(allscans)
+    t = torch.zeros((M, 2, 1080), dtype=torch.float32, device='cuda')
+    t[:, 1] = torch.from_numpy(allscans).cuda()
+    t[:, 0] = 7.0
+    act = torch.full((M, 2, 2), -9.0, dtype=torch.float32, device='cuda')
+    gap_follow_actions(t, act, agent_idx=1)
+    torch.cuda.synchronize()
+    a = act.cpu().numpy()
+    assert (a[:, 0] == -9.0).all()                                   # the ego slot is untouched
+    assert np.array_equal(a[:N, 1], g['actions'].astype(np.float32))
+    ref = np.stack([gap_follow_action(s) for s in more]).astype(np.float32)
+    assert np.array_equal(a[N:, 1], ref)
+
+
+def test_device_rollout_runs_without_host_sync():
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout, F110VecEnv
+    N = 64
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
+    poses = np.stack([cl[idx], cl[(idx + 40) % len(cl)]], axis=1)
+    env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'scans_f32', 'state'))
+    torch.manual_seed(42)
+    actor = Actor(1088, 2, [-0.4189, 0.0], [0.4189, 20.0]).cuda()
+    ro = DeviceRollout(env, actor)
+    ro.reset(poses)
+    for _ in range(50):
+        obs, r, term, trunc, info = ro.step()
+    torch.cuda.synchronize()
+    st = info['state'].cpu().numpy()
+    assert np.isfinite(st).all() and obs.shape == (N, 1088)
+    # the gap-follow opponent drives: it has moved and is below its 2.5 m/s command
+    assert (st[:, 1, 3] > 0.5).mean() > 0.5 and st[:, 1, 3].max() <= 2.6
+    env.close()

@@ -150,3 +150,14 @@ def test_map_not_set_and_bad_index():
         o.step()
     with pytest.raises(IndexError):
         o.update_params(DEFAULT_PARAMS, 5)
+
+
+def test_gap_follow_oracle_matches_reference():
+    """rl_training/utils/gap_follow.py:43-58 on 214 recorded / synthetic float32 scans: actions bit-exact."""
+    from oracle.f110_oracle import gap_follow_action
+    g = H.load('gap_follow')
+    for s, a in zip(g['scans'], g['actions']):
+        assert np.array_equal(gap_follow_action(s), a)
+    for k in range(len(g['proc'])):
+        _, p = gap_follow_action(g['scans'][k], want_proc=True)
+        assert np.array_equal(p, g['proc'][k])
