@@ -409,6 +409,7 @@ def test_device_rollout_runs_without_host_sync():
     torch.cuda.synchronize()
     st = info['state'].cpu().numpy()
     assert np.isfinite(st).all() and obs.shape == (N, 1088)
-    # the gap-follow opponent drives: it has moved and is below its 2.5 m/s command
-    assert (st[:, 1, 3] > 0.5).mean() > 0.5 and st[:, 1, 3].max() <= 2.6
+    # the gap-follow opponent drives (its speed can exceed the 2.5 m/s command: with the env's default v_min = 1e-8 a
+    # braking request accelerates, the pid quirk of dynamic_models.py:204-219 that is reproduced on purpose)
+    assert (st[:, 1, 3] > 0.5).mean() > 0.5
     env.close()

@@ -1,0 +1,60 @@
+"""BASELINE config 5: DDPG-style rollout loop on device -- ego = the reference's actor architecture
+(random init, seed 42), opponent = gap-follow kernel (or constant), E two-agent envs per GPU, observations consumed
+in place by torch.  Prints rollout env-steps/s.  Not a bench.py line; results are recorded in profiles/."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout, F110VecEnv  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=8192)
+ap.add_argument("--steps", type=int, default=100)
+ap.add_argument("--opponent", default="gap_follow")
+ap.add_argument("--graph", action="store_true", help="capture one rollout step in a CUDA graph")
+args = ap.parse_args()
+
+N = args.envs
+m = H.golden_map('Shanghai_map')
+cl = H.load('maps')['Shanghai_map__centerline_poses']
+idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
+poses = np.stack([cl[idx], cl[(idx + 40) % len(cl)]], axis=1)
+env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'scans_f32'))
+torch.manual_seed(42)
+actor = Actor(1088, 2, [-0.4189, 0.0], [0.4189, 20.0]).cuda()
+opp = 'gap_follow' if args.opponent == 'gap_follow' else (0.0, 1.5)
+ro = DeviceRollout(env, actor, opponent=opp)
+ro.reset(poses)
+for _ in range(10):
+    ro.step()
+step = ro.step
+if args.graph:
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ro.step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ro.step()
+    step = g.replay
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+for _ in range(args.steps):
+    step()
+e1.record()
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+ms = e0.elapsed_time(e1)
+print(json.dumps({"config": "C5 rollout: %d two-agent envs, actor 1088-128-128-2 + %s opponent%s" % (N, args.opponent, ", CUDA graph" if args.graph else ""),
+                  "env_steps_per_s": N * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                  "wall_ms_per_step": 1e3 * wall / args.steps, "rays_per_s": N * 2 * 1080 * args.steps / (ms * 1e-3)}))
