@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--host-chunks", type=int, default=4, help="env chunks pipelined by the e2e host path")
+    ap.add_argument("--host-chunks", type=int, default=2, help="env chunks pipelined by the e2e host path")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     return ap.parse_args()
 

@@ -21,7 +21,7 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 
 # every symbol include/f110_b200.h declares
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_tables",
-           "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync",
+           "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
            "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow"]
 
@@ -29,7 +29,7 @@ EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy",
 class F110Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("num_envs", C.c_int32), ("num_agents", C.c_int32),
                 ("num_beams", C.c_int32), ("theta_dis", C.c_int32), ("integrator", C.c_int32), ("ego_idx", C.c_int32),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("flags", C.c_uint32), ("host_stream_rank", C.c_uint32),
                 ("fov", C.c_double), ("eps", C.c_double), ("max_range", C.c_double), ("timestep", C.c_double),
                 ("lidar_dist", C.c_double), ("ttc_thresh", C.c_double), ("lidar_max", C.c_double),
                 ("noise_std", C.c_double), ("seed", C.c_uint64)]
@@ -71,6 +71,7 @@ def load():
     L.f110_step_host.argtypes = [vp, C.POINTER(F110StepIO)]
     L.f110_step_host_async.argtypes = [vp, C.POINTER(F110StepIO)]
     L.f110_host_sync.argtypes = [vp]
+    L.f110_step_host_multi.argtypes = [C.POINTER(vp), C.POINTER(F110StepIO), C.c_int32]
     L.f110_state_nbytes.argtypes = [vp]
     L.f110_state_nbytes.restype = C.c_int64
     L.f110_get_state.argtypes = [vp, vp, vp]

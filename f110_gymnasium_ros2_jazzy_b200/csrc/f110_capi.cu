@@ -194,7 +194,15 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     if (e == cudaSuccess) e = cudaMemset(sim->state_blob, 0, sim->state_bytes);
     if (e == cudaSuccess) e = cudaMemset(sim->scratch_blob, 0, sim->scratch_bytes);
     if (e == cudaSuccess) e = cudaMemset(sim->d_tables, 0, ntab * sizeof(double));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sim->host_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // host_stream_rank r > 0: the r-th highest stream priority the device offers, so that a caller pipelining several
+        // handles (f110_step_host_multi) gets handle 1's kernels finished -- and its download started -- first
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        int prio = least;
+        if (cfg->host_stream_rank > 0) { prio = greatest + (int)cfg->host_stream_rank - 1; if (prio > least) prio = least; }
+        e = cudaStreamCreateWithPriority(&sim->host_stream, cudaStreamNonBlocking, prio);
+    }
     if (e != cudaSuccess) {
         fail(F110_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
         f110_destroy(sim);
@@ -384,6 +392,19 @@ int f110_host_sync(F110Sim* sim) {
     if (!sim) return fail(F110_ERR_INVALID, "null handle");
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaStreamSynchronize(sim->host_stream));
+    return F110_OK;
+}
+
+int f110_step_host_multi(F110Sim* const* sims, const F110StepIO* ios, int32_t count) {
+    if (!sims || !ios || count < 1) return fail(F110_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < count; ++i) {
+        const int rc = f110_step_host_async(sims[i], &ios[i]);
+        if (rc != F110_OK) return rc;
+    }
+    for (int i = 0; i < count; ++i) {
+        const int rc = f110_host_sync(sims[i]);
+        if (rc != F110_OK) return rc;
+    }
     return F110_OK;
 }
 

@@ -247,7 +247,7 @@ class F110HostVecEnv(object):
     the other chunks' kernels.  Auto-reset as in F110VecEnv.
     """
 
-    def __init__(self, num_envs, chunks=4, map_arrays=None, map_dir=None, map=None, map_ext='.png', num_agents=1,
+    def __init__(self, num_envs, chunks=2, map_arrays=None, map_dir=None, map=None, map_ext='.png', num_agents=1,
                  seed=42, device=None, outputs=FAST_OUTPUTS, num_beams=1080, **kw):
         chunks = max(1, min(chunks, num_envs))
         self.num_envs, self.num_agents, self.num_beams = num_envs, num_agents, num_beams
@@ -255,7 +255,8 @@ class F110HostVecEnv(object):
         self.parts = []
         for k in range(chunks):
             n = self.bounds[k + 1] - self.bounds[k]
-            b = BatchSim(n, num_agents, seed=seed + 7919 * k, device=device, outputs=('obs',), num_beams=num_beams, **kw)
+            b = BatchSim(n, num_agents, seed=seed + 7919 * k, device=device, outputs=('obs',), num_beams=num_beams,
+                         host_stream_rank=k + 1, **kw)
             if map_arrays is not None:
                 b.set_map_arrays(*map_arrays)
             else:
@@ -272,13 +273,41 @@ class F110HostVecEnv(object):
         self._term_t = torch.ones(num_envs, dtype=torch.uint8, pin_memory=True)
         self._term = self._term_t.numpy()
 
-    def _run(self, actions, reset_mask):
-        for k, b in enumerate(self.parts):
-            lo, hi = self.bounds[k], self.bounds[k + 1]
-            b.step_host(None if actions is None else actions[lo:hi], None, reset_mask[lo:hi], self.start_poses[lo:hi],
-                        self._views[k], sync=False)
-        for b in self.parts:
-            b.host_sync()
+    def _build_ios(self):
+        """The F110StepIO of every chunk, built once: all buffers are persistent (pinned outputs, reset mask, start
+        poses); only the action pointer changes from step to step."""
+        import ctypes as C
+        from . import _lib
+        K = len(self.parts)
+        self._ios = (_lib.F110StepIO * K)()
+        self._handles = (C.c_void_p * K)(*[b.h for b in self.parts])
+        for k in range(K):
+            lo = self.bounds[k]
+            io = self._ios[k]
+            io.reset_mask = self._term_t.data_ptr() + lo
+            io.reset_poses = self._poses_t.data_ptr() + lo * self.num_agents * 3 * 8
+            for key, t in self._views[k].items():
+                setattr(io, key, t.data_ptr())
+        self._lib = _lib
+
+    def _run(self, actions):
+        K = len(self.parts)
+        if actions is None:
+            for k in range(K):
+                self._ios[k].actions = None
+        else:
+            a = np.ascontiguousarray(actions)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            assert a.size == self.num_envs * self.num_agents * 2
+            item = a.dtype.itemsize * self.num_agents * 2
+            base = a.ctypes.data
+            f64 = int(a.dtype == np.float64)
+            for k in range(K):
+                self._ios[k].actions = base + self.bounds[k] * item
+                self._ios[k].actions_f64 = f64
+            self._keep = a
+        self._lib.check(self._lib.load().f110_step_host_multi(self._handles, self._ios, K))
         return self.out
 
     def reset(self, poses):
@@ -288,14 +317,15 @@ class F110HostVecEnv(object):
         self._poses_t = torch.from_numpy(np.ascontiguousarray(p)).pin_memory()
         self.start_poses = self._poses_t.numpy()
         self._term[:] = 1
-        o = self._run(None, self._term)
+        self._build_ios()
+        o = self._run(None)
         return o['obs'].numpy(), o
 
     def step(self, actions):
         """actions: numpy (or pinned tensor viewed as numpy) [N, A, 2] f32/f64."""
         # the previous step's `terminated` (still in the pinned output buffer) is this step's reset mask
         np.copyto(self._term, self.out['terminated'].numpy())
-        o = self._run(actions, self._term)
+        o = self._run(actions)
         return o['obs'].numpy(), o['reward'].numpy(), o['terminated'].numpy(), None, o
 
     def close(self):

@@ -81,7 +81,7 @@ typedef struct F110Config {
     int32_t integrator;    /* F110_INTEGRATOR_* (f110_env.py:176-179) */
     int32_t ego_idx;       /* f110_env.py:170-173 */
     uint32_t flags;
-    uint32_t reserved;
+    uint32_t host_stream_rank; /* 0: default priority for the f110_step_host* stream; r > 0: r-th highest priority */
     double fov;            /* 4.7 rad (base_classes.py:69) */
     double eps;            /* 1e-4 ray-march termination (laser_models.py:360) */
     double max_range;      /* 30.0 m (laser_models.py:360) */
@@ -152,6 +152,9 @@ int f110_step_host(F110Sim* sim, const F110StepIO* io);
  * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels. */
 int f110_step_host_async(F110Sim* sim, const F110StepIO* io);
 int f110_host_sync(F110Sim* sim);
+/* f110_step_host_async on `count` handles (ios[i] belongs to sims[i]), then f110_host_sync on each: one call per step
+ * for a caller that shards its envs over several handles. */
+int f110_step_host_multi(F110Sim* const* sims, const F110StepIO* ios, int32_t count);
 
 /* Checkpoint of the whole persistent simulation state as one opaque blob (DEVICE pointer). */
 int64_t f110_state_nbytes(const F110Sim* sim);
