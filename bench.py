@@ -320,11 +320,14 @@ def main():
             peaks = json.load(open(pk_path))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / (lidar_ms * 1e-3) / 1e9
+        gather = gather_roofline(map_arrays[0], E * A * B, lbar, torch, dev)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
                     "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar,
                     "bytes_per_ray": bytes_per_ray, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                    "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]}}
+                    "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]},
+                    "gather_roofline": dict(gather, frac_of_whole_map=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["whole_map_gbs"],
+                                            frac_of_touched_window=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["touched_window_gbs"])}
         # ---- CPU arm beside it
         cpu = None
         if not args.no_cpu_baseline:
@@ -391,6 +394,25 @@ def e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch):
     el = time.perf_counter() - t0
     henv.close()
     return el
+
+
+def gather_roofline(dt, rays, lbar, torch, dev):
+    """Empirical dependent-gather roofline: f110_gather_probe with the lidar kernel's thread count and a
+    chain of round(L-bar) dependent 8-byte loads, over the whole map (L2-resident random gather) and over a 4 MiB
+    window (about what 4096 cars on the track actually touch).  GB/s of useful 8-byte cells."""
+    import ctypes as C
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    L = _lib.load()
+    m = torch.from_numpy(np.ascontiguousarray(dt)).to(dev)
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    chain = max(1, int(round(lbar)))
+    out = {"chain": chain, "threads": int(rays)}
+    for key, window in (("whole_map_gbs", 0), ("touched_window_gbs", 512 * 1024)):
+        ms = C.c_float(0)
+        _lib.check(L.f110_gather_probe(C.c_void_p(m.data_ptr()), m.numel(), window, chain, int(rays), 5,
+                                       C.c_void_p(sink.data_ptr()), C.byref(ms), None))
+        out[key] = 8.0 * chain * rays / (ms.value * 1e-3) / 1e9
+    return out
 
 
 def load_traffic():

@@ -23,7 +23,7 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_tables",
            "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
-           "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow"]
+           "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe"]
 
 
 class F110Config(C.Structure):
@@ -82,6 +82,7 @@ def load():
     L.f110_get_kernel_timing.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.f110_gap_follow.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, C.c_double, C.c_double, C.c_float,
                                   C.c_int32, C.c_int32, C.c_float, vp]
+    L.f110_gather_probe.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int32, vp, C.POINTER(C.c_float), vp]
     L.f110_kernel_launches.argtypes = [vp]
     L.f110_kernel_launches.restype = C.c_int64
     if L.f110_abi_version() != F110_ABI_VERSION:

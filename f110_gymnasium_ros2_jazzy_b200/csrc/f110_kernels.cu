@@ -148,8 +148,16 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
         // of the buffers; its length was latched into heavy_cnt[0] by the post kernel) as this step's order.  A copy
         // rather than a pointer flip, so a captured CUDA graph stays valid step after step.
         const unsigned stride = gridDim.x * blockDim.x;
-        for (unsigned k = s; k < sc.num_units / 4; k += stride)   // num_units is padded to a multiple of 4
-            reinterpret_cast<uint32_t*>(sc.unit_heavy)[k] = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units)[k];
+        const unsigned nw = sc.num_units / 4;                        // num_units is padded to a multiple of 4
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units);
+        uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sc.unit_heavy);
+        for (unsigned base = s; base < nw; base += 8 * stride) {     // 8 independent loads in flight per thread
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; v[j] = k < nw ? src[k] : 0u; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; if (k < nw) dst[k] = v[j]; }
+        }
         const unsigned n = sc.heavy_cnt[0];
         for (unsigned k = s; k < n; k += stride) sc.heavy_list[k] = sc.heavy_list[sc.front_units + k];
     }

@@ -189,6 +189,13 @@ int f110_gap_follow(const float* scans, int64_t num_scans, int64_t scan_stride, 
                     float* actions, int64_t action_stride, double angle_min, double angle_increment,
                     float max_distance, int32_t window_size, int32_t bubble_radius, float threshold, void* stream);
 
+/* ---- measurement utility: the empirical dependent-gather roofline ----
+ * num_threads threads each chase `chain` dependent 8-byte loads through a power-of-two window of `window_cells`
+ * (<= 0: the whole map) cells of the DEVICE fp64 array map_dev; ms_out receives the average kernel time over
+ * `repeats` launches.  Synchronises. */
+int f110_gather_probe(const double* map_dev, int64_t num_cells, int64_t window_cells, int32_t chain,
+                      int64_t num_threads, int32_t repeats, double* sink_dev, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
