@@ -151,7 +151,7 @@ def cpu_arm(args, steps, warmup, envs=None, threads=None):
         threads = min(threads, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    n = envs or args.cpu_envs or max(64, 16 * threads)
+    n = envs or args.cpu_envs or max(256, 64 * threads)   # >= 64 envs per thread: amortises the per-step fork/join
     n = min(n, args.envs)
     map_arrays, poses = load_workload(args, n, 0, args.envs)
     o = Oracle(n, args.agents, num_beams=args.beams, noise_std=0.01, seed=42, threads=threads)
