@@ -23,7 +23,8 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_tables",
            "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
-           "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe"]
+           "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_reward_create", "f110_reward_destroy",
+           "f110_reward_compute"]
 
 
 class F110Config(C.Structure):
@@ -42,6 +43,14 @@ class F110StepIO(C.Structure):
                 ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("scans_f64", C.c_void_p),
                 ("scans_f32", C.c_void_p), ("state", C.c_void_p), ("collisions", C.c_void_p), ("toggles", C.c_void_p),
                 ("lap_times", C.c_void_p), ("lap_counts", C.c_void_p), ("time", C.c_void_p)]
+
+
+class F110RewardConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_envs", "num_points", "num_beams", "device", "closed", "grace_steps_wall",
+                                         "grace_steps_opp", "reserved")] + \
+               [(n, C.c_double) for n in ("dt", "w_prog", "forward_sign", "alive_bonus", "w_rel_lead", "lead_clip", "w_lat",
+                                          "lat_cap", "default_half_width", "lidar_max", "near_wall_dist", "w_wall",
+                                          "wall_quantile", "opp_safe_dist", "w_opp", "ego_crash_penalty", "opp_crash_bonus")]
 
 
 _lib = None
@@ -83,6 +92,10 @@ def load():
     L.f110_gap_follow.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, C.c_double, C.c_double, C.c_float,
                                   C.c_int32, C.c_int32, C.c_float, vp]
     L.f110_gather_probe.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int32, vp, C.POINTER(C.c_float), vp]
+    L.f110_reward_create.argtypes = [C.POINTER(F110RewardConfig), vp, vp, vp, C.POINTER(vp)]
+    L.f110_reward_destroy.argtypes = [vp]
+    L.f110_reward_destroy.restype = None
+    L.f110_reward_compute.argtypes = [vp, vp, vp, vp, vp, vp]
     L.f110_kernel_launches.argtypes = [vp]
     L.f110_kernel_launches.restype = C.c_int64
     if L.f110_abi_version() != F110_ABI_VERSION:

@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <vector>
 
 #include "f110_b200.h"
 
@@ -140,5 +143,396 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
     gap_follow_kernel<<<(unsigned)num_scans, GF_THREADS, 2 * sizeof(float) * num_beams, (cudaStream_t)stream>>>(
         scans, scan_stride, num_beams, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
         bubble_radius, threshold);
+    return cudaPeekAtLastError() == cudaSuccess ? F110_OK : F110_ERR_CUDA;
+}
+
+// =====================================================================================================================
+//   shaped_reward_kernel : rl_training/utils/rewards.py:185-355 (CenterlineSafetyProgressReward, with _Prog :86-180 and
+//                          parse_flat_obs :11-39) over rl_training/utils/track_progress.py (CenterlineProgress.project_xy
+//                          :58-95, delta_s :97-104) -- the reward train_ddpg.py:179 computes from the flat observation.
+//                          One CTA per env: brute-force 5-nearest segment midpoints for both cars (the reference's
+//                          cKDTree.query(k=5)), radix select for numpy's float32 quantile of the lidar, then one thread runs
+//                          the per-env progress state machine.  fp64 in the reference's order; results agree to ~1e-15.
+// =====================================================================================================================
+struct F110Reward {
+    F110RewardConfig cfg;
+    int n;
+    double L;
+    double *xy, *s, *tan, *nrm, *mid, *wR, *wL;   // device
+    void* state;                                  // device RewardState[N]
+    int device;
+};
+
+namespace {
+
+struct RewardState {
+    int has_s_prev[2], has_p_prev[2];
+    double s_prev[2], p_prev[2][2], cum[2], ema_abs, t_last[2], flip, buf_sum;
+    int buf_n, steps;
+};
+
+struct RewardView {
+    F110RewardConfig p;
+    int n;
+    double L;
+    const double *xy, *s, *tan, *nrm, *mid, *wR, *wL;
+    RewardState* st;
+};
+
+constexpr int RW_THREADS = 128;
+constexpr int KNN = 5;
+
+struct Cand { double d2; int idx; };
+__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx); }
+
+// sorted insertion into a register-resident top-5 (a thread visits increasing indices, so on equal distance the
+// earlier index stays ahead)
+__device__ __forceinline__ void topk_insert(Cand (&best)[KNN], double d2, int idx) {
+    if (!(d2 < best[KNN - 1].d2)) return;
+    best[KNN - 1].d2 = d2; best[KNN - 1].idx = idx;
+#pragma unroll
+    for (int j = KNN - 1; j > 0; --j) {
+        if (best[j].d2 < best[j - 1].d2) { const Cand t = best[j]; best[j] = best[j - 1]; best[j - 1] = t; }
+    }
+}
+
+// block-wide lexicographic min over (d2, idx); returns the winner to every thread
+__device__ Cand block_min_cand(Cand c, Cand* s_w) {
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand q;
+        q.d2 = __shfl_down_sync(0xffffffffu, c.d2, o);
+        q.idx = __shfl_down_sync(0xffffffffu, c.idx, o);
+        if (cand_less(q, c)) c = q;
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    Cand r = s_w[0];
+    for (int w = 1; w < RW_THREADS / 32; ++w) if (cand_less(s_w[w], r)) r = s_w[w];
+    __syncthreads();
+    return r;
+}
+
+// np.searchsorted(P.s, s, side="right") - 1 clamped to [0, n-2] (rewards.py:108-110, :272-274)
+__device__ int seg_index_at_s(const RewardView& v, double s) {
+    int lo = 0, hi = v.n;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (v.s[m] <= s) lo = m + 1; else hi = m; }
+    int idx = lo - 1;
+    idx = idx < 0 ? 0 : idx;
+    idx = idx > v.n - 2 ? v.n - 2 : idx;
+    return idx;
+}
+
+// project_xy (track_progress.py:58-95) on the K nearest midpoints, in ascending midpoint distance
+__device__ void project_on_candidates(const RewardView& v, const int* idx, int K, double x, double y, double& s_out, double& t_out) {
+    bool have = false;
+    double best_d = 0., best_s = 0., best_t = 0.;
+    for (int k = 0; k < K; ++k) {
+        const int i = idx[k];
+        if (i < 0) continue;
+        const double ax = v.xy[2 * i], ay = v.xy[2 * i + 1];
+        const double abx = v.xy[2 * i + 2] - ax, aby = v.xy[2 * i + 3] - ay;
+        const double L2 = abx * abx + aby * aby;
+        if (L2 <= 1e-12) continue;
+        const double apx = x - ax, apy = y - ay;
+        double tp = (apx * abx + apy * aby) / L2;
+        tp = tp < 0.0 ? 0.0 : (tp > 1.0 ? 1.0 : tp);
+        const double px = ax + tp * abx, py = ay + tp * aby;
+        const double s_proj = v.s[i] + tp * sqrt(abx * abx + aby * aby);
+        const double t_signed = (x - px) * v.nrm[2 * i] + (y - py) * v.nrm[2 * i + 1];
+        const double dist = sqrt((x - px) * (x - px) + (y - py) * (y - py));
+        if (!have || dist < best_d) { have = true; best_d = dist; best_s = s_proj; best_t = t_signed; }
+    }
+    if (!have) {   // degenerate fallback :90-93: snap to the nearest node
+        int j = 0;
+        double bd = INFINITY;
+        for (int i = 0; i < v.n; ++i) {
+            const double dx = v.xy[2 * i] - x, dy = v.xy[2 * i + 1] - y;
+            const double d = sqrt(dx * dx + dy * dy);
+            if (d < bd) { bd = d; j = i; }
+        }
+        s_out = v.s[j]; t_out = 0.0;
+        return;
+    }
+    s_out = best_s; t_out = best_t;
+}
+
+__device__ double signed_step(const RewardView& v, RewardState& r, int who, double x, double y, double s_curr, double s_prev) {
+    double ds_geom = s_curr - s_prev;                                   // delta_s, track_progress.py:97-104
+    if (v.p.closed) { if (ds_geom > 0.5 * v.L) ds_geom -= v.L; if (ds_geom < -0.5 * v.L) ds_geom += v.L; }
+    if (!r.has_p_prev[who]) { r.has_p_prev[who] = 1; r.p_prev[who][0] = x; r.p_prev[who][1] = y; return 0.0; }
+    const double dx = x - r.p_prev[who][0], dy = y - r.p_prev[who][1];
+    r.p_prev[who][0] = x; r.p_prev[who][1] = y;
+    const int idx = seg_index_at_s(v, s_curr);
+    const double ds_sign = dx * v.tan[2 * idx] + dy * v.tan[2 * idx + 1];
+    return copysign(fabs(ds_geom), fabs(ds_sign) > 1e-6 ? ds_sign : ds_geom);
+}
+
+__global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v, const float* __restrict__ obs,
+                                                                   const uint8_t* __restrict__ reset_mask,
+                                                                   double* __restrict__ out64, float* __restrict__ out32) {
+    const int env = blockIdx.x, tid = threadIdx.x;
+    const int B = v.p.num_beams;
+    const float* ob = obs + (size_t)env * (B + 8);
+    extern __shared__ unsigned s_bits[];            // [B] lidar as order-preserving unsigned
+    __shared__ Cand s_w[RW_THREADS / 32];
+    __shared__ int s_knn[2][KNN];
+    __shared__ double s_pose[5];                    // ex, ey, ox, oy, oth
+    __shared__ double s_proj[4];                    // e_s, e_t, o_s, o_t
+    __shared__ int s_flag[3];                       // early-out, steps, do-wall
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_sel[4];                   // prefix, remaining rank, count<=, min>
+    __shared__ float s_q[2];
+    RewardState& r = v.st[env];
+
+    if (tid == 0) {
+        if (reset_mask && reset_mask[env]) {        // reward_fn.reset() (rewards.py:262-264, _Prog.reset :98-106)
+            RewardState z;
+            memset(&z, 0, sizeof(z));
+            z.flip = +1.0;
+            r = z;
+        }
+        // parse_flat_obs :11-39 (the float32 fields are widened by float())
+        s_pose[0] = (double)ob[B + 0]; s_pose[1] = (double)ob[B + 1];
+        s_pose[2] = (double)ob[B + 4]; s_pose[3] = (double)ob[B + 5];
+        double th = (double)ob[B + 6] + 3.141592653589793;
+        double m = fmod(th, 2 * 3.141592653589793);
+        if (m != 0.0) { if (m < 0.0) m += 2 * 3.141592653589793; } else m = 0.0;
+        s_pose[4] = m - 3.141592653589793;
+        const bool ego_col = ob[B + 3] != 0.0f, opp_col = ob[B + 7] != 0.0f;
+        r.steps += 1;                                                   // :299
+        s_flag[1] = r.steps;
+        s_flag[0] = 0;
+        if (ego_col) { s_flag[0] = 1; if (out64) out64[env] = -v.p.ego_crash_penalty; if (out32) out32[env] = (float)-v.p.ego_crash_penalty; }
+        else if (opp_col && v.p.opp_crash_bonus > 0.0) { s_flag[0] = 1; if (out64) out64[env] = v.p.opp_crash_bonus; if (out32) out32[env] = (float)v.p.opp_crash_bonus; }
+        s_flag[2] = r.steps >= v.p.grace_steps_wall;
+    }
+    __syncthreads();
+    if (s_flag[0]) return;
+
+    // ---- 5 nearest midpoints of both cars (cKDTree.query(p, k=5)): per-thread top-5, then 5 block-wide pops
+    {
+        Cand be[KNN], bo[KNN];
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) { be[k].d2 = INFINITY; be[k].idx = 0x7fffffff; bo[k] = be[k]; }
+        const double ex = s_pose[0], ey = s_pose[1], ox = s_pose[2], oy = s_pose[3];
+        for (int i = tid; i < v.n - 1; i += RW_THREADS) {
+            const double mx = v.mid[2 * i], my = v.mid[2 * i + 1];
+            const double d1x = mx - ex, d1y = my - ey, d2x = mx - ox, d2y = my - oy;
+            topk_insert(be, d1x * d1x + d1y * d1y, i);
+            topk_insert(bo, d2x * d2x + d2y * d2y, i);
+        }
+        int he = 0, ho = 0;
+        for (int round = 0; round < KNN; ++round) {
+            Cand c;
+            c.d2 = INFINITY; c.idx = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) if (k == he) c = be[k];       // head of this thread's sorted list
+            const Cand w = block_min_cand(c, s_w);
+            if (w.idx == c.idx && w.d2 == c.d2 && c.idx != 0x7fffffff) ++he;
+            if (tid == 0) s_knn[0][round] = w.idx == 0x7fffffff ? -1 : w.idx;
+            c.d2 = INFINITY; c.idx = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < KNN; ++k) if (k == ho) c = bo[k];
+            const Cand w2 = block_min_cand(c, s_w);
+            if (w2.idx == c.idx && w2.d2 == c.d2 && c.idx != 0x7fffffff) ++ho;
+            if (tid == 0) s_knn[1][round] = w2.idx == 0x7fffffff ? -1 : w2.idx;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) project_on_candidates(v, s_knn[0], KNN, s_pose[0], s_pose[1], s_proj[0], s_proj[1]);
+    if (tid == 32) project_on_candidates(v, s_knn[1], KNN, s_pose[2], s_pose[3], s_proj[2], s_proj[3]);
+
+    // ---- np.quantile(rng, wall_q) of the float32 lidar (rewards.py:335-339): radix select of the two order statistics
+    if (s_flag[2]) {
+        const float lm = (float)v.p.lidar_max;
+        for (int i = tid; i < B; i += RW_THREADS) {
+            float x = ob[i];
+            if (x <= 0.0f || !isfinite(x)) x = lm;                      // zeros / NaNs count as far
+            x = x < 0.0f ? 0.0f : (x > lm ? lm : x);
+            s_bits[i] = __float_as_uint(x);                             // x >= 0: unsigned order == float order
+        }
+        const float vi = (float)(B - 1) * (float)v.p.wall_quantile;     // numpy forms the virtual index in float32
+        const int lo = (int)floorf(vi);
+        if (tid == 0) { s_sel[0] = 0u; s_sel[1] = (unsigned)lo; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int b = tid; b < 256; b += RW_THREADS) s_hist[b] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_sel[0];
+            const unsigned himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for (int i = tid; i < B; i += RW_THREADS) {
+                const unsigned u = s_bits[i];
+                if ((u & himask) == prefix) atomicAdd(&s_hist[(u >> shift) & 0xFFu], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned rank = s_sel[1], b = 0;
+                while (b < 255u && rank >= s_hist[b]) { rank -= s_hist[b]; ++b; }
+                s_sel[0] = prefix | (b << shift);
+                s_sel[1] = rank;
+            }
+            __syncthreads();
+        }
+        const unsigned vk = s_sel[0];                                   // bits of sorted[lo]
+        if (tid == 0) { s_sel[2] = 0u; s_sel[3] = 0xFFFFFFFFu; }
+        __syncthreads();
+        unsigned cnt = 0, mn = 0xFFFFFFFFu;
+        for (int i = tid; i < B; i += RW_THREADS) {
+            const unsigned u = s_bits[i];
+            if (u <= vk) ++cnt; else mn = u < mn ? u : mn;
+        }
+        atomicAdd(&s_sel[2], cnt);
+        atomicMin(&s_sel[3], mn);
+        __syncthreads();
+        if (tid == 0) {
+            const int hi = lo + 1 < B ? lo + 1 : B - 1;
+            const float a = __uint_as_float(vk);
+            const float b = (hi == lo || s_sel[2] >= (unsigned)(lo + 2)) ? a : __uint_as_float(s_sel[3]);
+            const float g = __fsub_rn(vi, (float)lo);
+            const float d = __fsub_rn(b, a);
+            // _lerp in float32: b - (b-a)*(1-g) for g >= 0.5, else a + (b-a)*g
+            s_q[0] = g >= 0.5f ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        const double ex = s_pose[0], ey = s_pose[1], ox = s_pose[2], oy = s_pose[3], oth = s_pose[4];
+        const double e_s = s_proj[0], e_t = s_proj[1], o_s = s_proj[2], o_t = s_proj[3];
+        // _Prog.update :129-167
+        if (!r.has_s_prev[0]) { r.has_s_prev[0] = 1; r.s_prev[0] = e_s; }
+        if (!r.has_s_prev[1]) { r.has_s_prev[1] = 1; r.s_prev[1] = o_s; }
+        double de = signed_step(v, r, 0, ex, ey, e_s, r.s_prev[0]);
+        double dop = signed_step(v, r, 1, ox, oy, o_s, r.s_prev[1]);
+        r.s_prev[0] = e_s; r.s_prev[1] = o_s;
+        if (r.buf_n < 20) {
+            r.buf_sum += de; r.buf_n += 1;
+            if (r.buf_n == 20 && r.buf_sum / 20 < 0.0) r.flip = -1.0;
+        }
+        de *= r.flip; dop *= r.flip;
+        r.cum[0] += de; r.cum[1] += dop;
+        r.ema_abs = 0.8 * r.ema_abs + (1.0 - 0.8) * fabs(de);
+        r.t_last[0] = e_t; r.t_last[1] = o_t;
+        const int steps = s_flag[1];
+        double dego = de;
+        if (steps < 10 && dego < 0.0) dego = 0.0;                        // :311-312
+        const double r_prog = v.p.w_prog * v.p.forward_sign * dego;
+        const double r_alive = v.p.alive_bonus;
+        double r_lead = 0.0;
+        if (v.p.w_rel_lead != 0.0) {
+            double lead = r.cum[0] - r.cum[1];
+            lead = lead < -v.p.lead_clip ? -v.p.lead_clip : (lead > v.p.lead_clip ? v.p.lead_clip : lead);
+            r_lead = v.p.w_rel_lead * (lead / v.p.lead_clip);
+        }
+        const int idx = seg_index_at_s(v, e_s);                          // lateral :323-333
+        double wR = v.p.default_half_width, wL = v.p.default_half_width;
+        if (v.wR && v.wL) { wR = v.wR[idx]; wL = v.wL[idx]; }
+        double w_eff = e_t >= 0.0 ? wL : wR;
+        w_eff = w_eff < 0.2 ? 0.2 : w_eff;
+        const double lat_norm = fabs(e_t) / w_eff;
+        const double lat_sq = lat_norm * lat_norm;
+        const double r_lat = -v.p.w_lat * (lat_sq < v.p.lat_cap ? lat_sq : v.p.lat_cap);
+        double r_wall = 0.0;                                             // :335-343
+        if (s_flag[2]) {
+            const double dmin = (double)s_q[0];
+            if (dmin < v.p.near_wall_dist) {
+                const double x = (v.p.near_wall_dist - dmin) / (v.p.near_wall_dist > 1e-6 ? v.p.near_wall_dist : 1e-6);
+                r_wall = -v.p.w_wall * (x * x);
+            }
+        }
+        double r_opp = 0.0;                                              // :345-352
+        if (steps >= v.p.grace_steps_opp) {
+            const double rho = hypot(ex - ox, ey - oy);
+            if (rho < v.p.opp_safe_dist) {
+                const double y = (v.p.opp_safe_dist - rho) / (v.p.opp_safe_dist > 1e-6 ? v.p.opp_safe_dist : 1e-6);
+                r_opp = -v.p.w_opp * (y * y);
+            }
+        }
+        double r_flank = 0.0;                                            // :353-358
+        {
+            const double dx = ex - ox, dy = ey - oy;
+            double sn, cs;
+            sincos(-oth, &sn, &cs);
+            const double x_rel = cs * dx - sn * dy, y_rel = sn * dx + cs * dy;
+            if (0.2 <= x_rel && x_rel <= 1.8 && 0.25 <= fabs(y_rel) && fabs(y_rel) <= 0.8) {
+                double yb = 0.8 - fabs(fabs(y_rel) - 0.525);
+                yb = yb < 0.0 ? 0.0 : yb;
+                r_flank = 0.1 * (x_rel / 1.8) * (yb / 0.8);
+            }
+        }
+        const double total = r_prog + r_alive + r_lead + r_lat + r_wall + r_opp + r_flank;
+        if (out64) out64[env] = total;
+        if (out32) out32[env] = (float)total;
+    }
+}
+
+}  // namespace
+
+extern "C" int f110_reward_create(const F110RewardConfig* cfg, const double* xy, const double* wR, const double* wL,
+                                  F110Reward** out) {
+    if (!cfg || !xy || !out || cfg->num_envs < 1 || cfg->num_points < 2 || cfg->num_beams < 1 || cfg->num_beams > 8192)
+        return F110_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return F110_ERR_NO_DEVICE; }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return F110_ERR_CUDA;
+    F110Reward* r = new F110Reward();
+    r->cfg = *cfg; r->n = cfg->num_points; r->device = cfg->device;
+    const int n = r->n;
+    // CenterlineProgress.__init__, track_progress.py:33-49 (host, once)
+    double* s = new double[n];
+    double* tan = new double[2 * (n - 1)];
+    double* nrm = new double[2 * (n - 1)];
+    double* mid = new double[2 * (n - 1)];
+    s[0] = 0.0;
+    for (int i = 0; i < n - 1; ++i) {
+        const double sx = xy[2 * i + 2] - xy[2 * i], sy = xy[2 * i + 3] - xy[2 * i + 1];
+        const double len = sqrt(sx * sx + sy * sy);
+        s[i + 1] = s[i] + len;
+        const double den = len > 1e-12 ? len : 1e-12;
+        tan[2 * i] = sx / den; tan[2 * i + 1] = sy / den;
+        nrm[2 * i] = -tan[2 * i + 1]; nrm[2 * i + 1] = tan[2 * i];
+        mid[2 * i] = (xy[2 * i] + xy[2 * i + 2]) * 0.5; mid[2 * i + 1] = (xy[2 * i + 1] + xy[2 * i + 3]) * 0.5;
+    }
+    r->L = s[n - 1];
+    auto up = [](const double* h, size_t cnt, double** d) {
+        if (cudaMalloc(d, cnt * sizeof(double)) != cudaSuccess) return false;
+        return cudaMemcpy(*d, h, cnt * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up(xy, 2 * (size_t)n, &r->xy) && up(s, n, &r->s) && up(tan, 2 * (size_t)(n - 1), &r->tan) &&
+              up(nrm, 2 * (size_t)(n - 1), &r->nrm) && up(mid, 2 * (size_t)(n - 1), &r->mid);
+    r->wR = r->wL = nullptr;
+    if (ok && wR && wL) ok = up(wR, n, &r->wR) && up(wL, n, &r->wL);
+    delete[] s; delete[] tan; delete[] nrm; delete[] mid;
+    if (ok) {
+        std::vector<RewardState> init(cfg->num_envs);
+        memset(init.data(), 0, sizeof(RewardState) * init.size());
+        for (auto& st : init) st.flip = +1.0;
+        ok = cudaMalloc(&r->state, sizeof(RewardState) * init.size()) == cudaSuccess &&
+             cudaMemcpy(r->state, init.data(), sizeof(RewardState) * init.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    cudaSetDevice(prev);
+    if (!ok) { f110_reward_destroy(r); return F110_ERR_CUDA; }
+    *out = r;
+    return F110_OK;
+}
+
+extern "C" void f110_reward_destroy(F110Reward* r) {
+    if (!r) return;
+    cudaFree(r->xy); cudaFree(r->s); cudaFree(r->tan); cudaFree(r->nrm); cudaFree(r->mid); cudaFree(r->wR); cudaFree(r->wL);
+    cudaFree(r->state);
+    delete r;
+}
+
+extern "C" int f110_reward_compute(F110Reward* r, const float* obs, const uint8_t* reset_mask, double* out_f64, float* out_f32,
+                                   void* stream) {
+    if (!r || !obs || (!out_f64 && !out_f32)) return F110_ERR_INVALID;
+    RewardView v;
+    v.p = r->cfg; v.n = r->n; v.L = r->L;
+    v.xy = r->xy; v.s = r->s; v.tan = r->tan; v.nrm = r->nrm; v.mid = r->mid; v.wR = r->wR; v.wL = r->wL;
+    v.st = static_cast<RewardState*>(r->state);
+    shaped_reward_kernel<<<r->cfg.num_envs, RW_THREADS, sizeof(unsigned) * r->cfg.num_beams, (cudaStream_t)stream>>>(
+        v, obs, reset_mask, out_f64, out_f32);
     return cudaPeekAtLastError() == cudaSuccess ? F110_OK : F110_ERR_CUDA;
 }

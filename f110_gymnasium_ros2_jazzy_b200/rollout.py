@@ -87,3 +87,67 @@ class DeviceRollout(object):
             gap_follow_actions(self.env.backend.out['scans_f32'], self.actions, agent_idx=1)
         self.obs, reward, terminated, truncated, info = self.env.step(self.actions)
         return self.obs, reward, terminated, truncated, info
+
+
+# CenterlineSafetyProgressReward.__init__ defaults (rl_training/utils/rewards.py:196-222)
+REWARD_DEFAULTS = dict(dt=0.01, w_prog=1.2, forward_sign=+1.0, alive_bonus=0.02, w_rel_lead=0.0, lead_clip=5.0, w_lat=0.35,
+                       lat_cap=4.0, default_half_width=1.5, lidar_max=1.0, near_wall_dist=0.35 / 30.0, w_wall=1.0,
+                       wall_quantile=0.05, opp_safe_dist=0.7, w_opp=0.8, ego_crash_penalty=50.0, opp_crash_bonus=50.0,
+                       grace_steps_wall=25, grace_steps_opp=25)
+
+
+class ShapedReward(object):
+    """Batched CenterlineSafetyProgressReward (rewards.py:185-355) on a CenterlineProgress (track_progress.py): one
+    independent reward object per env, evaluated by ``f110_reward_compute`` straight from the observation tensor.
+
+    ``centerline``: [n, 2] (x_m, y_m) or [n, 4] (+ w_tr_right_m, w_tr_left_m), the CSV train_ddpg.py loads.  Keyword
+    arguments are the reference constructor's.  ``__call__(obs, reset_mask=None)`` returns a float64 CUDA tensor [N];
+    ``reset_mask`` plays the role of ``reward_fn.reset()`` per env.
+    """
+
+    def __init__(self, num_envs, centerline, num_beams=1080, closed=True, device=None, **kw):
+        unknown = set(kw) - set(REWARD_DEFAULTS)
+        if unknown:
+            raise TypeError("unknown reward arguments: %s" % sorted(unknown))
+        p = dict(REWARD_DEFAULTS)
+        p.update(kw)
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        cl = np.ascontiguousarray(centerline, np.float64)
+        xy = np.ascontiguousarray(cl[:, :2])
+        wR = np.ascontiguousarray(cl[:, 2]) if cl.shape[1] >= 4 else None
+        wL = np.ascontiguousarray(cl[:, 3]) if cl.shape[1] >= 4 else None
+        cfg = _lib.F110RewardConfig(num_envs=num_envs, num_points=len(xy), num_beams=num_beams, device=self.device.index,
+                                    closed=int(closed), grace_steps_wall=int(p['grace_steps_wall']),
+                                    grace_steps_opp=int(p['grace_steps_opp']),
+                                    **{k: float(v) for k, v in p.items() if not k.startswith('grace_')})
+        h = C.c_void_p()
+        _lib.check(self.lib.f110_reward_create(C.byref(cfg), xy.ctypes.data_as(C.c_void_p),
+                                               None if wR is None else wR.ctypes.data_as(C.c_void_p),
+                                               None if wL is None else wL.ctypes.data_as(C.c_void_p), C.byref(h)))
+        self.h = h
+        self.N, self.B = num_envs, num_beams
+        self.out = torch.zeros(num_envs, dtype=torch.float64, device=self.device)
+
+    def __call__(self, obs, reset_mask=None):
+        if not (obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.N * (self.B + 8)):
+            raise ValueError("obs must be a contiguous CUDA float32 tensor [N, B+8]")
+        rm = None
+        if reset_mask is not None:
+            rm = reset_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            self._keep = rm
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.f110_reward_compute(self.h, C.c_void_p(obs.data_ptr()), None if rm is None else C.c_void_p(rm.data_ptr()),
+                                                C.c_void_p(self.out.data_ptr()), None, stream))
+        return self.out
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.f110_reward_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

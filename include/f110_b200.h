@@ -189,6 +189,24 @@ int f110_gap_follow(const float* scans, int64_t num_scans, int64_t scan_stride, 
                     float* actions, int64_t action_stride, double angle_min, double angle_increment,
                     float max_distance, int32_t window_size, int32_t bubble_radius, float threshold, void* stream);
 
+/* CenterlineSafetyProgressReward (rl_training/utils/rewards.py:185-355) over CenterlineProgress
+ * (rl_training/utils/track_progress.py), the reward train_ddpg.py:127-145,179 computes from the flat observation; one
+ * independent reward object (progress tracker state included) per env.  Field names and defaults are the constructor's. */
+typedef struct F110RewardConfig {
+    int32_t num_envs, num_points, num_beams, device;
+    int32_t closed;             /* CenterlineProgress(closed=True) */
+    int32_t grace_steps_wall, grace_steps_opp, reserved;
+    double dt, w_prog, forward_sign, alive_bonus, w_rel_lead, lead_clip, w_lat, lat_cap, default_half_width, lidar_max,
+           near_wall_dist, w_wall, wall_quantile, opp_safe_dist, w_opp, ego_crash_penalty, opp_crash_bonus;
+} F110RewardConfig;
+typedef struct F110Reward F110Reward;
+/* xy: HOST [num_points][2] centerline; wR / wL: HOST [num_points] half-widths or NULL (CSV columns w_tr_right_m / _left_m). */
+int f110_reward_create(const F110RewardConfig* cfg, const double* xy, const double* wR, const double* wL, F110Reward** out);
+void f110_reward_destroy(F110Reward* r);
+/* obs: DEVICE float [num_envs][num_beams + 8] (F110StepIO.obs); reset_mask: DEVICE [num_envs] or NULL, non-zero =
+ * reward_fn.reset() before this call; out_f64 / out_f32: DEVICE [num_envs], either may be NULL. */
+int f110_reward_compute(F110Reward* r, const float* obs, const uint8_t* reset_mask, double* out_f64, float* out_f32, void* stream);
+
 /* ---- measurement utility: the empirical dependent-gather roofline ----
  * num_threads threads each chase `chain` dependent 8-byte loads through a power-of-two window of `window_cells`
  * (<= 0: the whole map) cells of the DEVICE fp64 array map_dev; ms_out receives the average kernel time over

@@ -910,3 +910,246 @@ void f110o_gap_follow(const float* scan, int n, double angle_min, double angle_i
     *steer_out = steering; *speed_out = speed; *best_out = best;
     free(proc);
 }
+
+/* ------------------------------------------------------------------ shaped reward
+ * rl_training/utils/rewards.py: parse_flat_obs :11-39, _Prog :86-180, CenterlineSafetyProgressReward :185-355;
+ * rl_training/utils/track_progress.py: CenterlineProgress.__init__ :17-55, project_xy :58-95, delta_s :97-104.
+ * Paths relative to /root/reference/.  One independent reward object per env (the reference has one env). */
+typedef struct {
+    int has_s_prev[2], has_p_prev[2];
+    double s_prev[2], p_prev[2][2], cum[2], ema_abs, t_last[2], flip, buf_sum;
+    int buf_n, steps;
+} RewardState;
+
+typedef struct F110RewardOracle {
+    int N, n, closed, has_widths, B;
+    double *xy, *s, *tan, *nrm, *mid, *wR, *wL;   /* [n][2], [n], [n-1][2] x3, [n], [n] */
+    double L;
+    double dt, w_prog, forward_sign, alive_bonus, w_rel_lead, lead_clip, w_lat, lat_cap, default_half_width, lidar_max,
+           near_wall_dist, w_wall, wall_q, opp_safe_dist, w_opp, ego_crash_penalty, opp_crash_bonus;
+    int grace_wall, grace_opp;
+    RewardState* st;
+} F110RewardOracle;
+
+static void reward_state_reset(RewardState* r) {   /* _Prog.reset :98-106 + reward reset :262-264 */
+    memset(r, 0, sizeof(*r));
+    r->flip = +1.0;
+}
+
+F110RewardOracle* f110o_reward_create(int N, int B, const double* xy, const double* wR, const double* wL, int n, int closed,
+                                      const double* p /*[17]*/, int grace_wall, int grace_opp) {
+    F110RewardOracle* o = (F110RewardOracle*)calloc(1, sizeof(*o));
+    o->N = N; o->n = n; o->closed = closed; o->B = B; o->has_widths = wR && wL;
+    o->xy = (double*)malloc(sizeof(double) * 2 * n); memcpy(o->xy, xy, sizeof(double) * 2 * n);
+    o->s = (double*)calloc(n, sizeof(double));
+    o->tan = (double*)malloc(sizeof(double) * 2 * (n - 1));
+    o->nrm = (double*)malloc(sizeof(double) * 2 * (n - 1));
+    o->mid = (double*)malloc(sizeof(double) * 2 * (n - 1));
+    for (int i = 0; i < n - 1; ++i) {             /* track_progress.py:33-49 */
+        double sx = xy[2 * i + 2] - xy[2 * i], sy = xy[2 * i + 3] - xy[2 * i + 1];
+        double len = sqrt(sx * sx + sy * sy);
+        o->s[i + 1] = o->s[i] + len;              /* np.cumsum: sequential */
+        double den = len > 1e-12 ? len : 1e-12;
+        o->tan[2 * i] = sx / den; o->tan[2 * i + 1] = sy / den;
+        o->nrm[2 * i] = -o->tan[2 * i + 1]; o->nrm[2 * i + 1] = o->tan[2 * i];
+        o->mid[2 * i] = (xy[2 * i] + xy[2 * i + 2]) * 0.5; o->mid[2 * i + 1] = (xy[2 * i + 1] + xy[2 * i + 3]) * 0.5;
+    }
+    o->L = o->s[n - 1];
+    if (o->has_widths) {
+        o->wR = (double*)malloc(sizeof(double) * n); memcpy(o->wR, wR, sizeof(double) * n);
+        o->wL = (double*)malloc(sizeof(double) * n); memcpy(o->wL, wL, sizeof(double) * n);
+    }
+    o->dt = p[0]; o->w_prog = p[1]; o->forward_sign = p[2]; o->alive_bonus = p[3]; o->w_rel_lead = p[4]; o->lead_clip = p[5];
+    o->w_lat = p[6]; o->lat_cap = p[7]; o->default_half_width = p[8]; o->lidar_max = p[9]; o->near_wall_dist = p[10];
+    o->w_wall = p[11]; o->wall_q = p[12]; o->opp_safe_dist = p[13]; o->w_opp = p[14]; o->ego_crash_penalty = p[15];
+    o->opp_crash_bonus = p[16];
+    o->grace_wall = grace_wall; o->grace_opp = grace_opp;
+    o->st = (RewardState*)malloc(sizeof(RewardState) * N);
+    for (int e = 0; e < N; ++e) reward_state_reset(&o->st[e]);
+    return o;
+}
+
+void f110o_reward_destroy(F110RewardOracle* o) {
+    if (!o) return;
+    free(o->xy); free(o->s); free(o->tan); free(o->nrm); free(o->mid); free(o->wR); free(o->wL); free(o->st); free(o);
+}
+
+/* project_xy, track_progress.py:58-95: the 5 nearest segment midpoints (cKDTree.query, ascending distance), best
+ * orthogonal projection among them (first strictly smaller distance wins) */
+static void project_xy(const F110RewardOracle* o, double x, double y, double* s_out, double* t_out) {
+    int K = o->n - 1 < 5 ? o->n - 1 : 5;
+    int idx[5]; double dd[5];
+    for (int k = 0; k < K; ++k) { idx[k] = -1; dd[k] = INFINITY; }
+    for (int i = 0; i < o->n - 1; ++i) {
+        double dx = o->mid[2 * i] - x, dy = o->mid[2 * i + 1] - y;
+        double d2 = dx * dx + dy * dy;
+        if (d2 < dd[K - 1]) {
+            int k = K - 1;
+            while (k > 0 && dd[k - 1] > d2) { dd[k] = dd[k - 1]; idx[k] = idx[k - 1]; --k; }
+            dd[k] = d2; idx[k] = i;
+        }
+    }
+    int have = 0; double best_d = 0, best_s = 0, best_t = 0;
+    for (int k = 0; k < K; ++k) {
+        int i = idx[k];
+        if (i < 0) continue;
+        double ax = o->xy[2 * i], ay = o->xy[2 * i + 1];
+        double abx = o->xy[2 * i + 2] - ax, aby = o->xy[2 * i + 3] - ay;
+        double L2 = abx * abx + aby * aby;
+        if (L2 <= 1e-12) continue;
+        double apx = x - ax, apy = y - ay;
+        double tp = (apx * abx + apy * aby) / L2;
+        tp = tp < 0.0 ? 0.0 : (tp > 1.0 ? 1.0 : tp);
+        double px = ax + tp * abx, py = ay + tp * aby;
+        double s_proj = o->s[i] + tp * sqrt(abx * abx + aby * aby);
+        double t_signed = (x - px) * o->nrm[2 * i] + (y - py) * o->nrm[2 * i + 1];
+        double dist = sqrt((x - px) * (x - px) + (y - py) * (y - py));
+        if (!have || dist < best_d) { have = 1; best_d = dist; best_s = s_proj; best_t = t_signed; }
+    }
+    if (!have) {   /* degenerate fallback :90-93 */
+        int j = 0; double bd = INFINITY;
+        for (int i = 0; i < o->n; ++i) {
+            double dx = o->xy[2 * i] - x, dy = o->xy[2 * i + 1] - y;
+            double d = sqrt(dx * dx + dy * dy);
+            if (d < bd) { bd = d; j = i; }
+        }
+        *s_out = o->s[j]; *t_out = 0.0; return;
+    }
+    *s_out = best_s; *t_out = best_t;
+}
+
+/* np.searchsorted(P.s, s, side="right") - 1, clamped to [0, n-2] (rewards.py:108-110, :272-274) */
+static int seg_index_at_s(const F110RewardOracle* o, double s) {
+    int lo = 0, hi = o->n;
+    while (lo < hi) { int m = (lo + hi) / 2; if (o->s[m] <= s) lo = m + 1; else hi = m; }
+    int idx = lo - 1;
+    if (idx < 0) idx = 0;
+    if (idx > o->n - 2) idx = o->n - 2;
+    return idx;
+}
+
+static double delta_s(const F110RewardOracle* o, double sc, double sp) {   /* track_progress.py:97-104 */
+    double ds = sc - sp;
+    if (o->closed) { if (ds > 0.5 * o->L) ds -= o->L; if (ds < -0.5 * o->L) ds += o->L; }
+    return ds;
+}
+
+static double signed_step(const F110RewardOracle* o, RewardState* r, int who, double x, double y, double s_curr, double s_prev) {
+    double ds_geom = delta_s(o, s_curr, s_prev);   /* rewards.py:113-127 */
+    if (!r->has_p_prev[who]) { r->has_p_prev[who] = 1; r->p_prev[who][0] = x; r->p_prev[who][1] = y; return 0.0; }
+    double dx = x - r->p_prev[who][0], dy = y - r->p_prev[who][1];
+    r->p_prev[who][0] = x; r->p_prev[who][1] = y;
+    int idx = seg_index_at_s(o, s_curr);
+    double ds_sign = dx * o->tan[2 * idx] + dy * o->tan[2 * idx + 1];
+    return copysign(fabs(ds_geom), fabs(ds_sign) > 1e-6 ? ds_sign : ds_geom);
+}
+
+static int cmp_f32(const void* a, const void* b) { float x = *(const float*)a, y = *(const float*)b; return (x > y) - (x < y); }
+
+/* np.quantile(float32 array, q), method 'linear': q and the virtual index are float32 (numpy converts q to the array
+ * dtype), gamma = vi - floor(vi) in float32, and _lerp evaluates b - (b-a)*(1-gamma) for gamma >= 0.5 else a + (b-a)*gamma,
+ * all in float32 */
+static float quantile_f32(float* v, int n, double q) {
+    qsort(v, n, sizeof(float), cmp_f32);
+    float vi = (float)(n - 1) * (float)q;
+    int lo = (int)floorf(vi);
+    int hi = lo + 1 < n ? lo + 1 : n - 1;
+    float g = vi - (float)lo;
+    float a = v[lo], b = v[hi], d = b - a;
+    return g >= 0.5f ? b - d * (1.0f - g) : a + d * g;
+}
+
+static double wrap_pi(double a) { return py_mod(a + PI, 2 * PI) - PI; }
+
+static double reward_one(const F110RewardOracle* o, RewardState* r, const float* obs) {
+    int B = o->B;
+    double ex = (double)obs[B + 0], ey = (double)obs[B + 1];
+    int ego_col = obs[B + 3] != 0.0f;
+    double ox = (double)obs[B + 4], oy = (double)obs[B + 5], oth = wrap_pi((double)obs[B + 6]);
+    int opp_col = obs[B + 7] != 0.0f;
+    r->steps += 1;                                                              /* :299 */
+    if (ego_col) return -o->ego_crash_penalty;                                  /* :302-303 */
+    if (opp_col && o->opp_crash_bonus > 0.0) return +o->opp_crash_bonus;        /* :304-305 */
+    /* _Prog.update :129-167 */
+    double e_s, e_t, o_s, o_t;
+    project_xy(o, ex, ey, &e_s, &e_t);
+    project_xy(o, ox, oy, &o_s, &o_t);
+    if (!r->has_s_prev[0]) { r->has_s_prev[0] = 1; r->s_prev[0] = e_s; }
+    if (!r->has_s_prev[1]) { r->has_s_prev[1] = 1; r->s_prev[1] = o_s; }
+    double de = signed_step(o, r, 0, ex, ey, e_s, r->s_prev[0]);
+    double dop = signed_step(o, r, 1, ox, oy, o_s, r->s_prev[1]);
+    r->s_prev[0] = e_s; r->s_prev[1] = o_s;
+    if (r->buf_n < 20) {
+        r->buf_sum += de; r->buf_n += 1;                                       /* sum(list) is sequential */
+        if (r->buf_n == 20 && r->buf_sum / 20 < 0.0) r->flip = -1.0;
+    }
+    de *= r->flip; dop *= r->flip;
+    r->cum[0] += de; r->cum[1] += dop;
+    r->ema_abs = 0.8 * r->ema_abs + (1.0 - 0.8) * fabs(de);
+    r->t_last[0] = e_t; r->t_last[1] = o_t;
+    double dego = de;
+    if (r->steps < 10 && dego < 0.0) dego = 0.0;                                /* :311-312 */
+    double r_prog = o->w_prog * o->forward_sign * dego;
+    double r_alive = o->alive_bonus;
+    double r_lead = 0.0;
+    if (o->w_rel_lead != 0.0) {
+        double lead = r->cum[0] - r->cum[1];
+        lead = lead < -o->lead_clip ? -o->lead_clip : (lead > o->lead_clip ? o->lead_clip : lead);
+        r_lead = o->w_rel_lead * (lead / o->lead_clip);
+    }
+    /* lateral :323-333 */
+    int idx = seg_index_at_s(o, e_s);
+    double wR = o->default_half_width, wL = o->default_half_width;
+    if (o->has_widths) { wR = o->wR[idx]; wL = o->wL[idx]; }
+    double w_eff = e_t >= 0.0 ? wL : wR;
+    if (w_eff < 0.2) w_eff = 0.2;
+    double lat_norm = fabs(e_t) / w_eff;
+    double lat_term = lat_norm * lat_norm < o->lat_cap ? lat_norm * lat_norm : o->lat_cap;
+    double r_lat = -o->w_lat * lat_term;
+    /* wall :335-343 */
+    double r_wall = 0.0;
+    if (r->steps >= o->grace_wall) {
+        float tmp[8192];
+        float lm = (float)o->lidar_max;
+        for (int i = 0; i < B; ++i) {
+            float v = obs[i];
+            if (v <= 0.0f || !isfinite(v)) v = lm;
+            v = v < 0.0f ? 0.0f : (v > lm ? lm : v);
+            tmp[i] = v;
+        }
+        double dmin = (double)quantile_f32(tmp, B, o->wall_q);
+        if (dmin < o->near_wall_dist) {
+            double x = (o->near_wall_dist - dmin) / (o->near_wall_dist > 1e-6 ? o->near_wall_dist : 1e-6);
+            r_wall = -o->w_wall * (x * x);
+        }
+    }
+    /* opponent bubble :345-352 */
+    double r_opp = 0.0;
+    if (r->steps >= o->grace_opp) {
+        double rho = hypot(ex - ox, ey - oy);
+        if (rho < o->opp_safe_dist) {
+            double y = (o->opp_safe_dist - rho) / (o->opp_safe_dist > 1e-6 ? o->opp_safe_dist : 1e-6);
+            r_opp = -o->w_opp * (y * y);
+        }
+    }
+    /* flank bonus :353-358 (_rot_into_opp_frame :62-67) */
+    double r_flank = 0.0;
+    {
+        double dx = ex - ox, dy = ey - oy;
+        double c = cos(-oth), s = sin(-oth);
+        double x_rel = c * dx - s * dy, y_rel = s * dx + c * dy;
+        if (0.2 <= x_rel && x_rel <= 1.8 && 0.25 <= fabs(y_rel) && fabs(y_rel) <= 0.8) {
+            double yb = 0.8 - fabs(fabs(y_rel) - 0.525);
+            if (yb < 0.0) yb = 0.0;
+            r_flank = 0.1 * (x_rel / 1.8) * (yb / 0.8);
+        }
+    }
+    return r_prog + r_alive + r_lead + r_lat + r_wall + r_opp + r_flank;
+}
+
+void f110o_reward_compute(F110RewardOracle* o, const float* obs /*[N][B+8]*/, const uint8_t* reset_mask, double* out) {
+    for (int e = 0; e < o->N; ++e) {
+        if (reset_mask && reset_mask[e]) reward_state_reset(&o->st[e]);
+        out[e] = reward_one(o, &o->st[e], obs + (size_t)e * (o->B + 8));
+    }
+}

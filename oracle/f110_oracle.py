@@ -65,6 +65,10 @@ def lib():
         L.f110o_collision.argtypes = [vp, vp]
         L.f110o_collision.restype = C.c_int
         L.f110o_collision_multiple.argtypes = [vp, C.c_int, vp, vp]
+        L.f110o_reward_create.restype = vp
+        L.f110o_reward_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+        L.f110o_reward_destroy.argtypes = [vp]
+        L.f110o_reward_compute.argtypes = [vp, vp, vp, vp]
         L.f110o_gap_follow.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_float, C.c_int, C.c_int, C.c_float,
                                        dp, dp, C.POINTER(C.c_int), vp]
         _LIB = L
@@ -284,3 +288,39 @@ def gap_follow_action(scan, angle_min=-np.pi / 2, angle_increment=np.pi / 1080, 
                        C.byref(best), _p(proc))
     out = np.array([st.value, sp.value])
     return (out, proc) if want_proc else out
+
+
+REWARD_PARAM_KEYS = ['dt', 'w_prog', 'forward_sign', 'alive_bonus', 'w_rel_lead', 'lead_clip', 'w_lat', 'lat_cap',
+                     'default_half_width', 'lidar_max', 'near_wall_dist', 'w_wall', 'wall_quantile', 'opp_safe_dist', 'w_opp',
+                     'ego_crash_penalty', 'opp_crash_bonus']
+# CenterlineSafetyProgressReward.__init__ defaults (rewards.py:196-222)
+REWARD_DEFAULTS = dict(dt=0.01, w_prog=1.2, forward_sign=+1.0, alive_bonus=0.02, w_rel_lead=0.0, lead_clip=5.0, w_lat=0.35,
+                       lat_cap=4.0, default_half_width=1.5, lidar_max=1.0, near_wall_dist=0.35 / 30.0, w_wall=1.0,
+                       wall_quantile=0.05, opp_safe_dist=0.7, w_opp=0.8, ego_crash_penalty=50.0, opp_crash_bonus=50.0,
+                       grace_steps_wall=25, grace_steps_opp=25)
+
+
+class RewardOracle(object):
+    """CenterlineSafetyProgressReward (rewards.py:185-355) over a CenterlineProgress (track_progress.py), one
+    independent instance per env.  centerline: [n, 4] rows x_m, y_m, w_tr_right_m, w_tr_left_m."""
+
+    def __init__(self, num_envs, centerline, num_beams=1080, closed=True, **kw):
+        self.L = lib()
+        p = dict(REWARD_DEFAULTS); p.update(kw)
+        cl = np.ascontiguousarray(centerline, np.float64)
+        xy = np.ascontiguousarray(cl[:, :2]); wR = np.ascontiguousarray(cl[:, 2]); wL = np.ascontiguousarray(cl[:, 3])
+        pv = np.array([float(p[k]) for k in REWARD_PARAM_KEYS])
+        self.N, self.B = num_envs, num_beams
+        self.h = self.L.f110o_reward_create(num_envs, num_beams, _p(xy), _p(wR), _p(wL), len(xy), int(closed), _p(pv),
+                                            int(p['grace_steps_wall']), int(p['grace_steps_opp']))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.L.f110o_reward_destroy(self.h); self.h = None
+
+    def __call__(self, obs, reset_mask=None):
+        obs = np.ascontiguousarray(obs, np.float32).reshape(self.N, self.B + 8)
+        out = np.empty(self.N)
+        rm = None if reset_mask is None else np.ascontiguousarray(reset_mask, np.uint8)
+        self.L.f110o_reward_compute(self.h, _p(obs), _p(rm), _p(out))
+        return out

@@ -210,9 +210,57 @@ def make_gap_follow_golden():
     print('gap_follow.npz', scans.shape, acts.dtype, proc.dtype)
 
 
+REWARD_KW = dict(w_prog=5.0, alive_bonus=0.5, grace_steps_wall=25, grace_steps_opp=175, w_lat=0.25, lat_cap=3.0,
+                 near_wall_dist=0.30 / 30, w_wall=0.30, wall_quantile=0.10, opp_safe_dist=0.60, w_opp=0.30,
+                 w_rel_lead=0.0)     # train_ddpg.py:127-145
+
+
+def make_reward_golden():
+    """train_ddpg.py:150-202 loop shape with the reference's own env, gap-follow opponent and shaped reward
+    (rewards.py:185-355 on CenterlineProgress, track_progress.py) -> tests/golden/reward.npz (obs + rewards)."""
+    sys.path.insert(0, os.path.join(REF_ROOT, 'rl_training'))
+    from utils.gap_follow import gap_follow_action
+    from utils.rewards import CenterlineSafetyProgressReward
+    from utils.track_progress import CenterlineProgress
+    csv = os.path.join(REF_ROOT, 'rl_training/maps/cenerlines/Shanghai_map.csv')
+    P = CenterlineProgress(csv, closed=True)
+    env = make_env(REF_MAPS, 'Shanghai_map')
+    rfn = CenterlineSafetyProgressReward(dt=env.timestep, progress=P, **REWARD_KW)
+    rfn2 = CenterlineSafetyProgressReward(dt=env.timestep, progress=P, w_rel_lead=0.3, grace_steps_wall=5, grace_steps_opp=5,
+                                          wall_quantile=0.05)   # defaults otherwise: exercises lead / bubble / flank terms
+    cl = np.loadtxt(csv, delimiter=',', comments='#')
+    rng = np.random.default_rng(21)
+    obs_all, rew_all, rew2_all, first = [], [], [], []
+    for ep, (i0, gap, kspeed) in enumerate([(0, 30, 1.6), (2500, 14, 1.2), (5200, 9, 2.2), (900, 12, 0.8)]):
+        def pose(i):
+            j = (i + 1) % len(cl)
+            return [cl[i, 0], cl[i, 1], np.arctan2(cl[j, 1] - cl[i, 1], cl[j, 0] - cl[i, 0])]
+        rfn.reset(); rfn2.reset()
+        obs, info = env.reset(options=np.array([pose(i0), pose((i0 + gap) % len(cl))], np.float32))
+        for t in range(260):
+            ego = gap_follow_action(info['scans'][0]).astype(np.float32)
+            ego[1] *= kspeed
+            ego[0] += np.float32(rng.normal(0, 0.03))
+            if ep == 3 and t > 120:
+                ego[0] = np.float32(0.35)        # drive it into the wall: crash penalty path
+            opp = gap_follow_action(info['scans'][1]).astype(np.float32)
+            obs, _, term, trunc, info = env.step(np.stack([ego, opp]).astype(np.float32))
+            obs_all.append(obs.copy()); rew_all.append(float(rfn(obs))); rew2_all.append(float(rfn2(obs)))
+            first.append(1 if t == 0 else 0)
+            if term and t > 150:
+                break
+    np.savez_compressed(os.path.join(HERE, 'reward.npz'), obs=np.stack(obs_all), reward=np.array(rew_all),
+                        reward_alt=np.array(rew2_all), episode_start=np.array(first, np.uint8),
+                        centerline=cl, s=P.s, L=np.float64(P.L))
+    print('reward.npz', len(rew_all), 'steps; reward range', min(rew_all), max(rew_all), 'alt', min(rew2_all), max(rew2_all))
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'gap_follow':
+    if len(sys.argv) > 1 and sys.argv[1] == 'reward':
+        make_reward_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'gap_follow':
         make_gap_follow_golden()     # only the consumer-side fixture
     else:
         main()
         make_gap_follow_golden()
+        make_reward_golden()

@@ -451,3 +451,31 @@ def test_c4_full_size_sharded_properties():
     for k in o1:
         assert torch.equal(o1[k], o2[k]), k
     sim.close()
+
+
+def test_shaped_reward_kernel_matches_reference_and_oracle():
+    """f110_reward_compute: (a) the recorded reference episodes, each replayed in its own env slot of one batch, (b) the
+    oracle on a seeded batch of independent envs.  Tolerance 1e-9 (fp64, device libm); crash returns are exact."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import ShapedReward
+    from oracle.f110_oracle import RewardOracle
+    from tests.test_oracle_golden import REWARD_ALT_KW, REWARD_KW
+    g = H.load('reward')
+    obs, starts = g['obs'], g['episode_start']
+    T = len(obs)
+    for kw, key in ((REWARD_KW, 'reward'), (REWARD_ALT_KW, 'reward_alt')):
+        # env slot 0 replays the recording; slots 1..3 replay it shifted in time (independent state per env)
+        N = 4
+        rw = ShapedReward(N, g['centerline'], **kw)
+        orc = RewardOracle(N, g['centerline'], **kw)
+        worst = 0.0
+        for t in range(T):
+            batch = np.stack([obs[(t + 37 * k) % T] for k in range(N)])
+            mask = np.array([starts[(t + 37 * k) % T] or t == 0 for k in range(N)], np.uint8)
+            got = rw(torch.from_numpy(batch).cuda(), torch.from_numpy(mask).cuda()).cpu().numpy()
+            ref = orc(batch, mask)
+            worst = max(worst, np.abs(got - ref).max())
+            assert abs(got[0] - g[key][t]) < 1e-9, (key, t, got[0], g[key][t])
+        assert worst < 1e-9
+        print('reward', key, 'worst vs oracle', worst)
+        rw.close()

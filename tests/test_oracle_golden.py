@@ -161,3 +161,21 @@ def test_gap_follow_oracle_matches_reference():
     for k in range(len(g['proc'])):
         _, p = gap_follow_action(g['scans'][k], want_proc=True)
         assert np.array_equal(p, g['proc'][k])
+
+
+REWARD_KW = dict(w_prog=5.0, alive_bonus=0.5, grace_steps_wall=25, grace_steps_opp=175, w_lat=0.25, lat_cap=3.0,
+                 near_wall_dist=0.30 / 30, w_wall=0.30, wall_quantile=0.10, opp_safe_dist=0.60, w_opp=0.30,
+                 w_rel_lead=0.0)       # train_ddpg.py:127-145
+REWARD_ALT_KW = dict(w_rel_lead=0.3, grace_steps_wall=5, grace_steps_opp=5, wall_quantile=0.05)
+
+
+def test_shaped_reward_oracle_matches_reference():
+    """rewards.py:185-355 + track_progress.py over 754 recorded steps (4 episodes incl. a crash), two parameter sets:
+    within 1e-12 of the reference's float (BLAS dots / libm ulps), and the float32 quantile path bit-exact."""
+    from oracle.f110_oracle import RewardOracle
+    g = H.load('reward')
+    for kw, key in ((REWARD_KW, 'reward'), (REWARD_ALT_KW, 'reward_alt')):
+        o = RewardOracle(1, g['centerline'], **kw)
+        got = np.array([o(g['obs'][k], np.array([g['episode_start'][k]], np.uint8))[0] for k in range(len(g[key]))])
+        assert np.abs(got - g[key]).max() < 1e-12
+        assert (got == -50.0).any() and (np.abs(got) < 5).any()
