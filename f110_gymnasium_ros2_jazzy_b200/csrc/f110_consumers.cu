@@ -159,6 +159,8 @@ struct F110Reward {
     int n;
     double L;
     double *xy, *s, *tan, *nrm, *mid, *wR, *wL;   // device
+    double* blk;                                  // device [nblk][3]: centre x, y and radius of 64 consecutive midpoints
+    int nblk;
     void* state;                                  // device RewardState[N]
     int device;
 };
@@ -175,41 +177,67 @@ struct RewardView {
     F110RewardConfig p;
     int n;
     double L;
-    const double *xy, *s, *tan, *nrm, *mid, *wR, *wL;
+    const double *xy, *s, *tan, *nrm, *mid, *wR, *wL, *blk;
+    int nblk;
     RewardState* st;
 };
 
 constexpr int RW_THREADS = 128;
 constexpr int KNN = 5;
+constexpr int MID_BLOCK = 64;   // midpoints per pruning block
 
 struct Cand { double d2; int idx; };
 __device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx); }
 
-// sorted insertion into a register-resident top-5 (a thread visits increasing indices, so on equal distance the
-// earlier index stays ahead)
+// sorted insertion into a register-resident top-5, ordered by (distance, index)
 __device__ __forceinline__ void topk_insert(Cand (&best)[KNN], double d2, int idx) {
-    if (!(d2 < best[KNN - 1].d2)) return;
-    best[KNN - 1].d2 = d2; best[KNN - 1].idx = idx;
+    Cand c;
+    c.d2 = d2; c.idx = idx;
+    if (!cand_less(c, best[KNN - 1])) return;
+    best[KNN - 1] = c;
 #pragma unroll
     for (int j = KNN - 1; j > 0; --j) {
-        if (best[j].d2 < best[j - 1].d2) { const Cand t = best[j]; best[j] = best[j - 1]; best[j - 1] = t; }
+        if (cand_less(best[j], best[j - 1])) { const Cand t = best[j]; best[j] = best[j - 1]; best[j - 1] = t; }
     }
 }
 
-// block-wide lexicographic min over (d2, idx); returns the winner to every thread
-__device__ Cand block_min_cand(Cand c, Cand* s_w) {
-    for (int o = 16; o > 0; o >>= 1) {
-        Cand q;
-        q.d2 = __shfl_down_sync(0xffffffffu, c.d2, o);
-        q.idx = __shfl_down_sync(0xffffffffu, c.idx, o);
-        if (cand_less(q, c)) c = q;
+// The KNN smallest (d2, idx) over the whole CTA.  Each warp pops its KNN best with shuffles (no barrier), the four
+// warps' lists meet in shared memory, thread 0 merges them.  `best` is this thread's sorted private list.
+__device__ void block_topk(const Cand (&best)[KNN], Cand* s_cand /*[4][KNN]*/, int* s_out /*[KNN]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int head = 0;
+    for (int round = 0; round < KNN; ++round) {
+        Cand c;
+        c.d2 = INFINITY; c.idx = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) if (k == head) c = best[k];
+        // warp-wide lexicographic min of (d2, idx) with three REDUX: d2 >= 0, so its bit pattern orders like the value
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(c.d2);
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+        const unsigned midx = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? (unsigned)c.idx : 0x7FFFFFFFu);
+        Cand w;
+        w.d2 = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        w.idx = (int)midx;
+        if (w.idx == c.idx && c.idx != 0x7fffffff) ++head;      // a midpoint index belongs to exactly one thread
+        if (lane == 0) s_cand[warp * KNN + round] = w;
     }
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
     __syncthreads();
-    Cand r = s_w[0];
-    for (int w = 1; w < RW_THREADS / 32; ++w) if (cand_less(s_w[w], r)) r = s_w[w];
+    if (threadIdx.x == 0) {
+        int h[RW_THREADS / 32] = { 0, 0, 0, 0 };
+        for (int round = 0; round < KNN; ++round) {
+            int bw = -1;
+            Cand bc;
+            bc.d2 = INFINITY; bc.idx = 0x7fffffff;
+            for (int w = 0; w < RW_THREADS / 32; ++w) {
+                if (h[w] < KNN && cand_less(s_cand[w * KNN + h[w]], bc)) { bc = s_cand[w * KNN + h[w]]; bw = w; }
+            }
+            if (bw >= 0) ++h[bw];
+            s_out[round] = bc.idx == 0x7fffffff ? -1 : bc.idx;
+        }
+    }
     __syncthreads();
-    return r;
 }
 
 // np.searchsorted(P.s, s, side="right") - 1 clamped to [0, n-2] (rewards.py:108-110, :272-274)
@@ -274,7 +302,11 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
     const int B = v.p.num_beams;
     const float* ob = obs + (size_t)env * (B + 8);
     extern __shared__ unsigned s_bits[];            // [B] lidar as order-preserving unsigned
-    __shared__ Cand s_w[RW_THREADS / 32];
+    __shared__ Cand s_cand[(RW_THREADS / 32) * KNN];
+    __shared__ double s_lb[256];                    // lower bound of every midpoint block (nblk <= 256)
+    __shared__ double s_tau[RW_THREADS / 32];
+    __shared__ int s_cblk[256];
+    __shared__ int s_ncand;
     __shared__ int s_knn[2][KNN];
     __shared__ double s_pose[5];                    // ex, ey, ox, oy, oth
     __shared__ double s_proj[4];                    // e_s, e_t, o_s, o_t
@@ -309,36 +341,47 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
     __syncthreads();
     if (s_flag[0]) return;
 
-    // ---- 5 nearest midpoints of both cars (cKDTree.query(p, k=5)): per-thread top-5, then 5 block-wide pops
-    {
-        Cand be[KNN], bo[KNN];
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) { be[k].d2 = INFINITY; be[k].idx = 0x7fffffff; bo[k] = be[k]; }
-        const double ex = s_pose[0], ey = s_pose[1], ox = s_pose[2], oy = s_pose[3];
-        for (int i = tid; i < v.n - 1; i += RW_THREADS) {
-            const double mx = v.mid[2 * i], my = v.mid[2 * i + 1];
-            const double d1x = mx - ex, d1y = my - ey, d2x = mx - ox, d2y = my - oy;
-            topk_insert(be, d1x * d1x + d1y * d1y, i);
-            topk_insert(bo, d2x * d2x + d2y * d2y, i);
+    // ---- 5 nearest midpoints of both cars (cKDTree.query(p, k=5)), exactly, without visiting all of them: the
+    // midpoints are grouped in blocks of 64 consecutive ones with a bounding circle (centre, R).  Any block holds >= 5
+    // points within |p - c| + R of p, so tau = min over blocks of that bound is an upper bound on the 5th-nearest
+    // distance, and only blocks with |p - c| - R <= tau can contain one of the 5.  On a race track that is 1-3 blocks.
+    for (int who = 0; who < 2; ++who) {
+        const double px = s_pose[2 * who], py = s_pose[2 * who + 1];
+        double ub = INFINITY;
+        for (int k = tid; k < v.nblk; k += RW_THREADS) {
+            const double dx = v.blk[3 * k] - px, dy = v.blk[3 * k + 1] - py, R = v.blk[3 * k + 2];
+            const double d = sqrt(dx * dx + dy * dy);
+            s_lb[k] = d - R;
+            const int cnt = min(MID_BLOCK, v.n - 1 - k * MID_BLOCK);
+            if (cnt >= KNN) ub = fmin(ub, d + R);
         }
-        int he = 0, ho = 0;
-        for (int round = 0; round < KNN; ++round) {
-            Cand c;
-            c.d2 = INFINITY; c.idx = 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) ub = fmin(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        if ((tid & 31) == 0) s_tau[tid >> 5] = ub;
+        __syncthreads();
+        double tau = fmin(fmin(s_tau[0], s_tau[1]), fmin(s_tau[2], s_tau[3]));
+        tau = tau * (1.0 + 1e-12) + 1e-12;                              // slack for the rounding of the bounds
+        Cand best[KNN];
 #pragma unroll
-            for (int k = 0; k < KNN; ++k) if (k == he) c = be[k];       // head of this thread's sorted list
-            const Cand w = block_min_cand(c, s_w);
-            if (w.idx == c.idx && w.d2 == c.d2 && c.idx != 0x7fffffff) ++he;
-            if (tid == 0) s_knn[0][round] = w.idx == 0x7fffffff ? -1 : w.idx;
-            c.d2 = INFINITY; c.idx = 0x7fffffff;
-#pragma unroll
-            for (int k = 0; k < KNN; ++k) if (k == ho) c = bo[k];
-            const Cand w2 = block_min_cand(c, s_w);
-            if (w2.idx == c.idx && w2.d2 == c.d2 && c.idx != 0x7fffffff) ++ho;
-            if (tid == 0) s_knn[1][round] = w2.idx == 0x7fffffff ? -1 : w2.idx;
+        for (int k = 0; k < KNN; ++k) { best[k].d2 = INFINITY; best[k].idx = 0x7fffffff; }
+        // compact the blocks that can hold one of the 5 (all of them if no block has 5 points)
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+        for (int k = tid; k < v.nblk; k += RW_THREADS)
+            if (!(tau < INFINITY) || s_lb[k] <= tau) s_cblk[atomicAdd(&s_ncand, 1)] = k;
+        __syncthreads();
+        const int ncand = s_ncand;
+        for (int j0 = 0; j0 < ncand; j0 += RW_THREADS / MID_BLOCK) {
+            const int j = j0 + tid / MID_BLOCK;                         // two blocks per pass
+            if (j < ncand) {
+                const int i = s_cblk[j] * MID_BLOCK + (tid % MID_BLOCK);
+                if (i < v.n - 1) {
+                    const double dx = v.mid[2 * i] - px, dy = v.mid[2 * i + 1] - py;
+                    topk_insert(best, dx * dx + dy * dy, i);
+                }
+            }
         }
+        block_topk(best, s_cand, s_knn[who]);
     }
-    __syncthreads();
     if (tid == 0) project_on_candidates(v, s_knn[0], KNN, s_pose[0], s_pose[1], s_proj[0], s_proj[1]);
     if (tid == 32) project_on_candidates(v, s_knn[1], KNN, s_pose[2], s_pose[3], s_proj[2], s_proj[3]);
 
@@ -365,11 +408,26 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
                 if ((u & himask) == prefix) atomicAdd(&s_hist[(u >> shift) & 0xFFu], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned rank = s_sel[1], b = 0;
-                while (b < 255u && rank >= s_hist[b]) { rank -= s_hist[b]; ++b; }
-                s_sel[0] = prefix | (b << shift);
-                s_sel[1] = rank;
+            if (tid < 32) {
+                // which of the 256 bins holds rank s_sel[1]?  lane l owns bins 8l..8l+7: warp scan of the lane sums, then
+                // the owning lane walks its own 8 bins
+                unsigned c[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[8 * tid + j]; sum += c[j]; }
+                unsigned incl = sum;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+                const unsigned rank = s_sel[1];
+                const unsigned excl = incl - sum;
+                const bool mine = rank >= excl && rank < incl;
+                const unsigned owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;   // counts sum to >= rank + 1: exists
+                __syncwarp();
+                if (tid == (int)owner) {
+                    unsigned rem = rank - excl, b = 0;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) if (b == (unsigned)j && rem >= c[j]) { rem -= c[j]; ++b; }
+                    s_sel[0] = prefix | ((8u * tid + b) << shift);
+                    s_sel[1] = rem;
+                }
             }
             __syncthreads();
         }
@@ -504,6 +562,21 @@ extern "C" int f110_reward_create(const F110RewardConfig* cfg, const double* xy,
               up(nrm, 2 * (size_t)(n - 1), &r->nrm) && up(mid, 2 * (size_t)(n - 1), &r->mid);
     r->wR = r->wL = nullptr;
     if (ok && wR && wL) ok = up(wR, n, &r->wR) && up(wL, n, &r->wL);
+    {   // bounding circles of MID_BLOCK consecutive midpoints
+        r->nblk = (n - 1 + MID_BLOCK - 1) / MID_BLOCK;
+        std::vector<double> blk(3 * (size_t)r->nblk);
+        for (int k = 0; k < r->nblk; ++k) {
+            const int i0 = k * MID_BLOCK, i1 = (k + 1) * MID_BLOCK < n - 1 ? (k + 1) * MID_BLOCK : n - 1;
+            double cx = 0, cy = 0;
+            for (int i = i0; i < i1; ++i) { cx += mid[2 * i]; cy += mid[2 * i + 1]; }
+            cx /= (i1 - i0); cy /= (i1 - i0);
+            double R = 0;
+            for (int i = i0; i < i1; ++i) { const double d = sqrt((mid[2 * i] - cx) * (mid[2 * i] - cx) + (mid[2 * i + 1] - cy) * (mid[2 * i + 1] - cy)); R = d > R ? d : R; }
+            blk[3 * k] = cx; blk[3 * k + 1] = cy; blk[3 * k + 2] = R * (1.0 + 1e-12) + 1e-12;
+        }
+        r->blk = nullptr;
+        if (ok) ok = r->nblk <= 256 && up(blk.data(), blk.size(), &r->blk);
+    }
     delete[] s; delete[] tan; delete[] nrm; delete[] mid;
     if (ok) {
         std::vector<RewardState> init(cfg->num_envs);
@@ -521,7 +594,7 @@ extern "C" int f110_reward_create(const F110RewardConfig* cfg, const double* xy,
 extern "C" void f110_reward_destroy(F110Reward* r) {
     if (!r) return;
     cudaFree(r->xy); cudaFree(r->s); cudaFree(r->tan); cudaFree(r->nrm); cudaFree(r->mid); cudaFree(r->wR); cudaFree(r->wL);
-    cudaFree(r->state);
+    cudaFree(r->blk); cudaFree(r->state);
     delete r;
 }
 
@@ -530,6 +603,7 @@ extern "C" int f110_reward_compute(F110Reward* r, const float* obs, const uint8_
     if (!r || !obs || (!out_f64 && !out_f32)) return F110_ERR_INVALID;
     RewardView v;
     v.p = r->cfg; v.n = r->n; v.L = r->L;
+    v.blk = r->blk; v.nblk = r->nblk;
     v.xy = r->xy; v.s = r->s; v.tan = r->tan; v.nrm = r->nrm; v.mid = r->mid; v.wR = r->wR; v.wL = r->wL;
     v.st = static_cast<RewardState*>(r->state);
     shaped_reward_kernel<<<r->cfg.num_envs, RW_THREADS, sizeof(unsigned) * r->cfg.num_beams, (cudaStream_t)stream>>>(

@@ -60,11 +60,12 @@ class Actor(torch.nn.Module):
 class DeviceRollout(object):
     """ego = policy(obs), opponent = gap-follow on its own scan, env.step -- no host round trip per step.
 
+    ``reward_fn`` (optional, e.g. ShapedReward) replaces the env's constant reward, as train_ddpg.py:179 does.
     ``env`` is an F110VecEnv with num_agents == 2 and 'scans_f32' among its outputs; ``policy`` maps the observation
     tensor [N, B+8] to ego actions [N, 2] (e.g. Actor).  ``opponent`` may be 'gap_follow' or a constant (steer, speed).
     """
 
-    def __init__(self, env, policy, opponent='gap_follow'):
+    def __init__(self, env, policy, opponent='gap_follow', reward_fn=None):
         if env.num_agents != 2:
             raise ValueError("DeviceRollout mirrors the reference's two-car loop (ego + opponent)")
         if opponent == 'gap_follow' and 'scans_f32' not in env.backend.out:
@@ -75,9 +76,12 @@ class DeviceRollout(object):
             self.actions[:, 1, 0] = float(opponent[0])
             self.actions[:, 1, 1] = float(opponent[1])
         self.obs = None
+        self.reward_fn = reward_fn          # e.g. ShapedReward: train_ddpg.py:179 discards the env's reward for it
+        self.reward = None
 
     def reset(self, poses):
-        self.obs, _ = self.env.reset(poses)
+        self.obs, o = self.env.reset(poses)
+        self._fresh = torch.ones(self.env.num_envs, dtype=torch.uint8, device=self.env.device)
         return self.obs
 
     @torch.no_grad()
@@ -85,7 +89,13 @@ class DeviceRollout(object):
         self.actions[:, 0, :] = self.policy(self.obs)
         if self.opponent == 'gap_follow':
             gap_follow_actions(self.env.backend.out['scans_f32'], self.actions, agent_idx=1)
+        if self.reward_fn is not None:
+            # an env that terminated on the previous step is auto-reset by this one: its reward object starts over too
+            self._fresh.copy_(self.env.backend.out['terminated'])
         self.obs, reward, terminated, truncated, info = self.env.step(self.actions)
+        if self.reward_fn is not None:
+            reward = self.reward_fn(self.obs, self._fresh)
+        self.reward = reward
         return self.obs, reward, terminated, truncated, info
 
 

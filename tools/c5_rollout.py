@@ -11,13 +11,14 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout, F110VecEnv  # noqa: E402
+from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout, F110VecEnv, ShapedReward  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=8192)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--opponent", default="gap_follow")
+ap.add_argument("--reward", action="store_true", help="also evaluate the shaped reward on device")
 ap.add_argument("--graph", action="store_true", help="capture one rollout step in a CUDA graph")
 args = ap.parse_args()
 
@@ -30,7 +31,12 @@ env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'termi
 torch.manual_seed(42)
 actor = Actor(1088, 2, [-0.4189, 0.0], [0.4189, 20.0]).cuda()
 opp = 'gap_follow' if args.opponent == 'gap_follow' else (0.0, 1.5)
-ro = DeviceRollout(env, actor, opponent=opp)
+rfn = None
+if args.reward:
+    rfn = ShapedReward(N, H.load('reward')['centerline'], w_prog=5.0, alive_bonus=0.5, grace_steps_wall=25, grace_steps_opp=175,
+                       w_lat=0.25, lat_cap=3.0, near_wall_dist=0.30 / 30, w_wall=0.30, wall_quantile=0.10, opp_safe_dist=0.60,
+                       w_opp=0.30)
+ro = DeviceRollout(env, actor, opponent=opp, reward_fn=rfn)
 ro.reset(poses)
 for _ in range(10):
     ro.step()
@@ -55,6 +61,6 @@ e1.record()
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 ms = e0.elapsed_time(e1)
-print(json.dumps({"config": "C5 rollout: %d two-agent envs, actor 1088-128-128-2 + %s opponent%s" % (N, args.opponent, ", CUDA graph" if args.graph else ""),
+print(json.dumps({"config": "C5 rollout: %d two-agent envs, actor 1088-128-128-2 + %s opponent%s%s" % (N, args.opponent, " + shaped reward" if args.reward else "", ", CUDA graph" if args.graph else ""),
                   "env_steps_per_s": N * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
                   "wall_ms_per_step": 1e3 * wall / args.steps, "rays_per_s": N * 2 * 1080 * args.steps / (ms * 1e-3)}))
