@@ -155,8 +155,8 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     if (!cfg || !params || !out) return fail(F110_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->abi_version != F110_ABI_VERSION) return fail(F110_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, F110_ABI_VERSION);
-    if (cfg->num_envs < 1 || cfg->num_agents < 1 || cfg->num_agents > F110_MAX_AGENTS || cfg->num_beams < 2 || cfg->theta_dis < 2)
-        return fail(F110_ERR_INVALID, "need num_envs >= 1, 1 <= num_agents <= %d, num_beams >= 2, theta_dis >= 2", F110_MAX_AGENTS);
+    if (cfg->num_envs < 1 || cfg->num_agents < 1 || cfg->num_agents > F110_MAX_AGENTS || cfg->num_beams < 32 || cfg->num_beams > 32768 || cfg->theta_dis < 2)
+        return fail(F110_ERR_INVALID, "need num_envs >= 1, 1 <= num_agents <= %d, 32 <= num_beams <= 32768, theta_dis >= 2", F110_MAX_AGENTS);
     if (cfg->ego_idx < 0 || cfg->ego_idx >= cfg->num_agents) return fail(F110_ERR_INDEX, "ego_idx out of range");
     if (cfg->integrator != F110_INTEGRATOR_RK4 && cfg->integrator != F110_INTEGRATOR_EULER)
         return fail(F110_ERR_INTEGRATOR, "Invalid Integrator Specified. Please choose RK4 or Euler");
