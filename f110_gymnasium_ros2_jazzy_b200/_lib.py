@@ -20,7 +20,7 @@ F110_ERR_INVALID, F110_ERR_MAP_NOT_SET, F110_ERR_CUDA, F110_ERR_INDEX = -1, -2, 
 F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 
 # every symbol include/f110_b200.h declares
-EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_tables",
+EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_map_image", "f110_get_map", "f110_set_tables",
            "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
            "f110_kernel_launches", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_reward_create", "f110_reward_destroy",
@@ -72,6 +72,8 @@ def load():
     L.f110_destroy.argtypes = [vp]
     L.f110_destroy.restype = None
     L.f110_set_map.argtypes = [vp, vp, C.c_int32, C.c_int32] + [C.c_double] * 5
+    L.f110_set_map_image.argtypes = [vp, vp, C.c_int32, C.c_int32] + [C.c_double] * 5
+    L.f110_get_map.argtypes = [vp, vp, C.c_int64]
     L.f110_set_tables.argtypes = [vp, vp, vp]
     L.f110_set_beam_tables.argtypes = [vp, vp, vp, vp]
     L.f110_set_params.argtypes = [vp, vp, C.c_int32]

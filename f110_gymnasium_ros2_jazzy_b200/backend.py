@@ -104,8 +104,27 @@ class BatchSim(object):
                                          float(np.cos(origin[2])), float(np.sin(origin[2]))))
         self.map_shape = dt.shape
 
-    def set_map(self, map_path, map_ext):
-        self.set_map_arrays(*load_map(map_path, map_ext))
+    def set_map_image(self, free_mask, resolution, origin):
+        """Map from the binarised image (non-zero = free, row 0 = bottom row): the EDT runs on the device
+        (f110_set_map_image) and reproduces resolution * scipy.ndimage.distance_transform_edt(img) bit for bit."""
+        m = np.ascontiguousarray(np.asarray(free_mask) != 0, np.uint8)
+        _lib.check(self.lib.f110_set_map_image(self.h, m.ctypes.data_as(C.c_void_p), m.shape[0], m.shape[1],
+                                               float(resolution), float(origin[0]), float(origin[1]),
+                                               float(np.cos(origin[2])), float(np.sin(origin[2]))))
+        self.map_shape = m.shape
+
+    def get_map(self):
+        dt = np.empty(self.map_shape, np.float64)
+        _lib.check(self.lib.f110_get_map(self.h, dt.ctypes.data_as(C.c_void_p), dt.size))
+        return dt
+
+    def set_map(self, map_path, map_ext, edt='host'):
+        """edt='host': scipy on the host, as the reference; edt='device': f110_set_map_image."""
+        if edt == 'device':
+            from .maps import load_map_image
+            self.set_map_image(*load_map_image(map_path, map_ext))
+        else:
+            self.set_map_arrays(*load_map(map_path, map_ext))
 
     def update_params(self, params, agent_idx=-1):
         pv = params_vector(params)

@@ -280,6 +280,46 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
     return F110_OK;
 }
 
+int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, int32_t width, double resolution,
+                       double orig_x, double orig_y, double orig_cos, double orig_sin) {
+    if (!sim || !free_mask || height < 1 || width < 1 || !(resolution > 0)) return fail(F110_ERR_INVALID, "bad map arguments");
+    if ((double)height * width >= 2147483648.0 || height >= 65536 || width >= 65536)
+        return fail(F110_ERR_INVALID, "map too large (need H*W < 2^31 and H, W < 65536)");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t cells = (size_t)height * width;
+    uint8_t* d_mask = nullptr;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d_mask, cells));
+    cudaError_t e = cudaMalloc(&d, cells * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_mask, free_mask, cells, cudaMemcpyHostToDevice);
+    int rc = -1;
+    if (e == cudaSuccess) rc = edt_device(d_mask, height, width, resolution, d, sim->host_stream);
+    cudaFree(d_mask);
+    if (e != cudaSuccess || rc != 0) { cudaFree(d); cudaGetLastError(); return fail(F110_ERR_CUDA, "device EDT failed"); }
+    cudaFree(sim->d_map);
+    sim->d_map = d;
+    MapView& m = sim->map;
+    m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
+    m.res = resolution; m.inv16 = (1.0 / resolution) * 65536.0;
+    m.w16 = (unsigned)width << 16; m.h16 = (unsigned)height << 16;
+    m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
+    m.wres = width * resolution; m.hres = height * resolution;
+    sim->map_set = true;
+    return F110_OK;
+}
+
+int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells) {
+    if (!sim || !dt_host) return fail(F110_ERR_INVALID, "null argument");
+    if (!sim->map_set) return fail(F110_ERR_MAP_NOT_SET, "Map is not set for scan simulator.");
+    const size_t cells = (size_t)sim->map.H * sim->map.W;
+    if ((size_t)capacity_cells < cells) return fail(F110_ERR_INVALID, "buffer too small for %d x %d cells", sim->map.H, sim->map.W);
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(dt_host, sim->d_map, cells * sizeof(double), cudaMemcpyDeviceToHost));
+    return F110_OK;
+}
+
 int f110_set_tables(F110Sim* sim, const double* sines, const double* cosines) {
     if (!sim || !sines || !cosines) return fail(F110_ERR_INVALID, "null argument");
     Guard g(sim->cfg.device);

@@ -87,3 +87,6 @@ void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const
                   bool count_lookups, int threads_per_block, cudaStream_t s);
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s);
 void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s);
+
+// exact EDT on the device (f110_edt.cu): freemask DEVICE [H][W] (non-zero = free), dt DEVICE fp64 [H][W]; synchronises
+int edt_device(const uint8_t* freemask, int H, int W, double resolution, double* dt, cudaStream_t stream);

@@ -132,6 +132,13 @@ void f110_destroy(F110Sim* sim);
  * laser_models.py:398-425 builds it; orig_cos/orig_sin = cos/sin(origin yaw) as computed by the host. */
 int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
                  double orig_x, double orig_y, double orig_cos, double orig_sin);
+/* The same from the binarised image itself: free_mask HOST uint8 [height][width], non-zero = free (pixel > 128), row 0 =
+ * bottom image row (laser_models.py:398-404).  The exact Euclidean distance transform (scipy's, laser_models.py:52) runs on
+ * the device in integers; the resulting fp64 map is bit-identical to resolution * distance_transform_edt(img). */
+int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, int32_t width, double resolution,
+                       double orig_x, double orig_y, double orig_cos, double orig_sin);
+/* Reads the handle's fp64 map back into dt_host (capacity in cells). */
+int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells);
 /* HOST [theta_dis] tables (laser_models.py:379-381). */
 int f110_set_tables(F110Sim* sim, const double* sines, const double* cosines);
 /* HOST [B] tables (base_classes.py:125-158).  scan_angles must be strictly increasing. */

@@ -479,3 +479,39 @@ def test_shaped_reward_kernel_matches_reference_and_oracle():
         assert worst < 1e-9
         print('reward', key, 'worst vs oracle', worst)
         rw.close()
+
+
+def test_device_edt_bit_identical_to_scipy():
+    """f110_set_map_image: the exact integer EDT on the device reproduces resolution * scipy.ndimage.distance_transform_edt
+    (laser_models.py:40-53) bit for bit -- on the three fixture maps and on random occupancy with thin / isolated obstacles."""
+    _torch()
+    from scipy.ndimage import distance_transform_edt
+    from f110_gymnasium_ros2_jazzy_b200 import BatchSim
+    sim = BatchSim(1, 1)
+    m = H.load('maps')
+    for name in ('Shanghai_map', 'straight_corridor', 'open_square'):
+        shape = tuple(int(v) for v in m[name + '__shape'])
+        free = np.unpackbits(m[name + '__bits'])[:shape[0] * shape[1]].reshape(shape)
+        ref, res, origin = H.golden_map(name)
+        sim.set_map_image(free, res, origin)
+        got = sim.get_map()
+        assert got.shape == ref.shape and np.array_equal(got, ref), name
+    rng = np.random.default_rng(4)
+    for shape, p in (((257, 131), 0.01), ((64, 700), 0.2), ((300, 300), 0.0005), ((5, 1000), 0.05)):
+        free = (rng.uniform(size=shape) > p).astype(np.uint8)
+        free[rng.integers(0, shape[0]), rng.integers(0, shape[1])] = 0      # at least one obstacle
+        ref = 0.0731 * distance_transform_edt(np.where(free, 255., 0.))
+        sim.set_map_image(free, 0.0731, [0.0, 0.0, 0.0])
+        assert np.array_equal(sim.get_map(), ref), shape
+    # and the scans taken on a device-built map equal the ones on the host-built map
+    g = H.load('scans')
+    poses = g['Shanghai_map__poses']
+    be = GpuBackend(len(poses), 1, 'Shanghai_map')
+    shape = tuple(int(v) for v in m['Shanghai_map__shape'])
+    free = np.unpackbits(m['Shanghai_map__bits'])[:shape[0] * shape[1]].reshape(shape)
+    _, res, origin = H.golden_map('Shanghai_map')
+    be.sim.set_map_image(free, res, origin)
+    be.sim.sim_reset(poses[:, None, :])
+    out = be.step(None, np.zeros((len(poses), 1, 1080)))
+    assert np.array_equal(out['scans'][:, 0], g['Shanghai_map__scans'])
+    sim.close()
