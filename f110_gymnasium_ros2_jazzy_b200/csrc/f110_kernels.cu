@@ -625,9 +625,16 @@ __device__ __forceinline__ double get_range(double ox, double oy, double v3x, do
     const double denom = v2x * v3x + v2y * v3y;
     double distance = INFINITY;
     if (fabs(denom) > 0.0) {
-        const double d1 = (v2x * v1y - v2y * v1x) / denom;
-        const double d2 = (v1x * v3x + v1y * v3y) / denom;
-        if (d1 >= 0.0 && d2 >= 0.0 && d2 <= 1.0) distance = d1;
+        // the reference forms d1 = cross/denom and d2 = dot/denom and accepts d1 >= 0 && 0 <= d2 <= 1.  Those tests do not
+        // need the quotients: a rounded quotient is >= 0 (-0.0 included) iff the numerator is zero or has the divisor's
+        // sign, and it is <= 1 iff |numerator| <= |divisor| (a larger numerator is at least one ulp larger, so the quotient
+        // rounds above 1).  Most edges are missed by the beam, so the one division left is rarely executed.
+        const double crs = v2x * v1y - v2y * v1x;
+        const double dot = v1x * v3x + v1y * v3y;
+        const bool neg = denom < 0.0;
+        const bool d1_ok = crs == 0.0 || ((crs < 0.0) == neg);
+        const bool d2_ok = (dot == 0.0 || ((dot < 0.0) == neg)) && fabs(dot) <= fabs(denom);
+        if (d1_ok && d2_ok) distance = crs / denom;
     } else {
         const double bax = vax - ox, bay = vay - oy;
         const double cax = ox - vbx, cay = oy - vby;
