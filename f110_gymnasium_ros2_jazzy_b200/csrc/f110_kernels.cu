@@ -846,12 +846,13 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     // beams inside some opponent's blocked-view window can get shorter, so only those are re-read (fp64 scratch
     // copy), lowered and re-written.
     const float lm = c.lidar_max;
-    for (int q = 0; q < epc * A * A; ++q) {
-        const int le = q / (A * A), u = q - le * A * A;
-        if (!s_active[le]) continue;
-        const EnvSmem e = env_smem(s_dyn + le * stride, A);
-        const int a = u / A;
-        const int env = env0 + le;
+    for (int le = 0; le < epc; ++le) {
+      if (!s_active[le]) continue;
+      const EnvSmem e = env_smem(s_dyn + le * stride, A);
+      const int env = env0 + le;
+      for (int a = 0, u = 0; a < A; ++a)
+      for (int b = 0; b < A; ++b, ++u) {           // nested counters: no integer divisions in this 24-trip loop
+        if (a == b) continue;
         const double* v = e.verts[u];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -879,6 +880,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
                 }
             }
         }
+      }
     }
     __syncthreads();
 
