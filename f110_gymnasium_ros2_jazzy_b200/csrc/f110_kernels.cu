@@ -142,6 +142,7 @@ __device__ __forceinline__ void pid(double speed, double steer, double cur_speed
 // ---------------------------------------------------------------- K1: dynamics
 
 __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    cudaGridDependencySynchronize();   // PDL: the previous step's post kernel (or whatever precedes in the stream) is done
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     {
         // Publish the launch-order history the lidar kernel recorded during the previous step (the "next" halves
@@ -381,6 +382,7 @@ __device__ __forceinline__ float obs_lidar(double range, float lm) {
 // DIRECT: A == 1 (env == s, no opponent ray-cast can follow, no fp64 scratch copy of the scan)
 template <bool COUNT, bool IDENT, bool DIRECT>
 __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
+    cudaGridDependencySynchronize();   // PDL: everything below reads what the dynamics kernel (and the previous step) wrote
     const unsigned total = (unsigned)c.NA * (unsigned)c.B;
     // ---- work-unit selection (one unit = 32 consecutive rays = one warp).  Ray lengths are heavy-tailed (median 4
     // lookups, p99 42, max ~300 on the Shanghai map), so a long ray that starts in the last wave of CTAs leaves
@@ -683,6 +685,7 @@ __host__ __device__ constexpr int post_envs_per_cta(int A) {
 }
 
 __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    cudaGridDependencySynchronize();
     const int A = c.A, B = c.B;
     const int tid = threadIdx.x;
     const int epc = post_envs_per_cta(A);
@@ -920,6 +923,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
 // K3 for A == 1: nothing to ray-cast and no pair to test, the lidar kernel already wrote the scans -> one thread
 // per env applies the iTTC consequence and the finish-zone / done bookkeeping (same statements as post_kernel).
 __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+    cudaGridDependencySynchronize();
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env == 0) latch_launch_order(sc);
     if (env >= c.N) return;
@@ -980,16 +984,29 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
 
 }  // namespace
 
+// Launch with programmatic stream serialisation (PDL): the grid may be scheduled while the previous kernel of the stream
+// drains; the kernel itself waits in cudaGridDependencySynchronize() before it touches anything that kernel wrote.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     const int threads = 128;
-    dynamics_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, sc, io);
+    launch_pdl(dynamics_kernel, dim3((c.NA + threads - 1) / threads), dim3(threads), 0, s, c, st, sc, io);
 }
 
 template <bool COUNT, bool IDENT>
 static void launch_lidar_t(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc,
                            const F110StepIO& io, unsigned blocks, unsigned threads, cudaStream_t s) {
-    if (c.A == 1) lidar_kernel<COUNT, IDENT, true><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
-    else lidar_kernel<COUNT, IDENT, false><<<blocks, threads, 0, s>>>(c, m, st, sc, io);
+    if (c.A == 1) launch_pdl(lidar_kernel<COUNT, IDENT, true>, dim3(blocks), dim3(threads), 0, s, c, m, st, sc, io);
+    else launch_pdl(lidar_kernel<COUNT, IDENT, false>, dim3(blocks), dim3(threads), 0, s, c, m, st, sc, io);
 }
 
 void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
@@ -1008,10 +1025,10 @@ void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const
 }
 
 void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
-    if (c.A == 1) post_single_kernel<<<(c.N + 127) / 128, 128, 0, s>>>(c, st, sc, io);
+    if (c.A == 1) launch_pdl(post_single_kernel, dim3((c.N + 127) / 128), dim3(128), 0, s, c, st, sc, io);
     else {
         const int epc = post_envs_per_cta(c.A);
-        post_kernel<<<(c.N + epc - 1) / epc, POST_THREADS, sizeof(double) * post_smem_doubles(c.A) * epc, s>>>(c, st, sc, io);
+        launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS), sizeof(double) * post_smem_doubles(c.A) * epc, s, c, st, sc, io);
     }
 }
 
