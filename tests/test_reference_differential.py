@@ -1,0 +1,63 @@
+"""Differential tests of the oracle against the LIVE reference (only where /root/reference exists, i.e. the build
+container; skipped on the GPU box).  The committed golden fixtures pin fixed scenarios; these draw fresh ones."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+from ref_loader import REF_MAPS, fresh_statics, load_reference, reference_available  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.filterwarnings('ignore')
+    return load_reference()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_rollout_oracle_vs_live_reference(ref, seed):
+    """Fresh start poses on the centerline, fresh random f32 actions, 250 steps: state and flat obs bit-exact, flags exact,
+    scans within 1e-12 (BLAS dots in the reference's opponent ray-cast)."""
+    from oracle.f110_oracle import Oracle
+    rng = np.random.default_rng(seed)
+    cl = np.loadtxt(os.path.join(os.path.dirname(REF_MAPS.rstrip('/')), 'maps/cenerlines/Shanghai_map.csv'), delimiter=',', comments='#')
+    i = int(rng.integers(0, len(cl) - 60))
+    def pose(k):
+        return [cl[k, 0], cl[k, 1], np.arctan2(cl[k + 1, 1] - cl[k, 1], cl[k + 1, 0] - cl[k, 0])]
+    poses = np.array([pose(i), pose(i + int(rng.integers(8, 50)))])
+    fresh_statics(ref)
+    env = ref.F110Env(map_dir=REF_MAPS, map='Shanghai_map', map_ext='.png', num_agents=2)
+    o = Oracle(1, 2)
+    o.set_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+    noise = np.random.default_rng(42)
+    obs, info = env.reset(options=poses)
+    nz = noise.normal(0., 0.01, size=1080)
+    out = o.reset(poses[None], noise=np.stack([nz, nz])[None])
+    assert np.array_equal(obs, out['obs'][0])
+    for t in range(250):
+        act = rng.uniform([-0.4189, 0], [0.4189, 9], size=(2, 2)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(act)
+        nz = noise.normal(0., 0.01, size=1080)
+        out = o.step(act[None], noise=np.stack([nz, nz])[None])
+        st = np.stack([a.state for a in env.sim.agents])
+        assert np.array_equal(st, out['state'][0]), t
+        assert np.array_equal(obs, out['obs'][0]), t
+        assert bool(out['terminated'][0]) == term and np.array_equal(info['collisions'], out['collisions'][0])
+        assert np.array_equal(env.toggle_list, out['toggles'][0])
+        assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
+
+
+def test_gap_follow_and_reward_vs_live_reference(ref):
+    from oracle.f110_oracle import RewardOracle, gap_follow_action
+    sys.path.insert(0, os.path.join(os.path.dirname(REF_MAPS.rstrip('/'))))
+    from utils.gap_follow import gap_follow_action as ref_gf
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        s = rng.uniform(0, 6, 1080).astype(np.float32)
+        s[rng.integers(0, 1000):][:rng.integers(1, 80)] = rng.uniform(0, 0.4)
+        assert np.array_equal(gap_follow_action(s), ref_gf(s.copy()))
