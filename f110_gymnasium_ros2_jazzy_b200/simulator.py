@@ -48,6 +48,7 @@ class Simulator(object):
         self._rngs = None
         self._pending_reset = None
         self.last = None
+        self._host_out = None
 
     def set_map(self, map_path, map_ext):
         self.backend.set_map(map_path, map_ext, edt=self.edt)
@@ -62,6 +63,7 @@ class Simulator(object):
         if poses.shape[0] != self.num_agents:
             raise ValueError('Number of poses for reset does not match number of agents.')
         self.backend.sim_reset(poses[None])
+        torch.cuda.current_stream(self.backend.device).synchronize()   # the host-buffer step runs on the library's own stream
         self._rngs = [np.random.default_rng(seed=self.seed) for _ in range(self.num_agents)]
 
     def _noise(self):
@@ -72,9 +74,13 @@ class Simulator(object):
         return np.stack([r.normal(0., 0.01, size=self.num_beams) for r in self._rngs])[None]
 
     def _step_raw(self, control_inputs, reset_mask=None, reset_poses=None):
-        out = self.backend.step(control_inputs, self._noise(), reset_mask, reset_poses)
-        torch.cuda.current_stream(self.backend.device).synchronize()
-        self.last = {k: v.cpu().numpy() for k, v in out.items()}
+        """One f110_step_host call: actions / noise up, kernels, every output down into pinned buffers, one sync.
+        The returned arrays are views of those buffers (rewritten by the next step); callers copy what they keep."""
+        if self._host_out is None:
+            self._host_out = self.backend.host_out(ALL_OUTPUTS)
+            self._host_np = {k: v.numpy() for k, v in self._host_out.items()}
+        self.backend.step_host(control_inputs, self._noise(), reset_mask, reset_poses, out=self._host_out)
+        self.last = self._host_np
         return self.last
 
     def step(self, control_inputs):
