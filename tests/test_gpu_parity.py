@@ -515,3 +515,27 @@ def test_device_edt_bit_identical_to_scipy():
     out = be.step(None, np.zeros((len(poses), 1, 1080)))
     assert np.array_equal(out['scans'][:, 0], g['Shanghai_map__scans'])
     sim.close()
+
+
+def test_ros_bridge_call_pattern(tmp_path):
+    """jazzy_bridge/.../gym_bridge.py:77-80,112-114,226-228,264-280: make(map=<path without extension>, map_ext, num_agents),
+    reset(options=...), step(float64 (A, 2)), then obs[0] / obs[1] as per-agent scans and info['poses_*'][i].  The reference's
+    own env returns a flat vector there (so the bridge cannot index it); obs_mode='scans' is the documented shim."""
+    _torch()
+    import f110_gymnasium_ros2_jazzy_b200 as f
+    map_dir, name = H.write_map_files('open_square', str(tmp_path))
+    env = f.make('f110_gym:f110-v0', map=map_dir + name, map_ext='.png', num_agents=2, obs_mode='scans')
+    obs, info = env.reset(options=np.array([[0.0, 0.0, 0.0], [2.0, 0.5, 0.0]]))
+    ego_scan, opp_scan = list(obs[0]), list(obs[1])
+    assert len(ego_scan) == 1080 and len(opp_scan) == 1080
+    for _ in range(5):
+        obs, reward, terminated, truncated, info = env.step(np.array([[0.1, 1.0], [0.0, 1.5]]))   # float64, as the bridge sends
+    assert obs.shape == (2, 1080) and obs.dtype == np.float32
+    assert float(info['poses_x'][1]) > 2.0 and abs(float(info['linear_vels_y'][0])) == 0.0
+    assert np.isfinite(info['ang_vels_z']).all() and info['poses_theta'].shape == (2,)
+    # single-agent form (gym_bridge.py:124,226)
+    env1 = f.make('f110_gym:f110-v0', map=map_dir + name, map_ext='.png', num_agents=1, obs_mode='scans')
+    obs, info = env1.reset(options=np.array([[0.0, 0.0, 0.0]]))
+    obs, reward, terminated, truncated, info = env1.step(np.array([[0.0, 1.0]]))
+    assert len(list(obs[0])) == 1080
+    env.close(); env1.close()
