@@ -240,19 +240,23 @@ __device__ void block_topk(const Cand (&best)[KNN], Cand* s_cand /*[4][KNN]*/, i
     __syncthreads();
 }
 
-// np.searchsorted(P.s, s, side="right") - 1 clamped to [0, n-2] (rewards.py:108-110, :272-274)
-__device__ int seg_index_at_s(const RewardView& v, double s) {
-    int lo = 0, hi = v.n;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (v.s[m] <= s) lo = m + 1; else hi = m; }
-    int idx = lo - 1;
+// np.searchsorted(P.s, s, side="right") - 1 clamped to [0, n-2] (rewards.py:108-110, :272-274).  s is non-decreasing and the
+// caller knows the segment the point was projected on, so the answer is found by walking from that hint (0-1 steps)
+// instead of a 13-step binary search of dependent loads.
+__device__ int seg_index_at_s(const RewardView& v, double s, int hint) {
+    int idx = hint < 0 ? 0 : (hint > v.n - 1 ? v.n - 1 : hint);
+    while (idx + 1 <= v.n - 1 && v.s[idx + 1] <= s) ++idx;     // largest idx with s[idx] <= s ...
+    while (idx > 0 && v.s[idx] > s) --idx;                     // ... from either side
+    if (idx == 0 && v.s[0] > s) idx = -1;                      // searchsorted(...) - 1 == -1 below the first knot
     idx = idx < 0 ? 0 : idx;
     idx = idx > v.n - 2 ? v.n - 2 : idx;
     return idx;
 }
 
 // project_xy (track_progress.py:58-95) on the K nearest midpoints, in ascending midpoint distance
-__device__ void project_on_candidates(const RewardView& v, const int* idx, int K, double x, double y, double& s_out, double& t_out) {
+__device__ int project_on_candidates(const RewardView& v, const int* idx, int K, double x, double y, double& s_out, double& t_out) {
     bool have = false;
+    int best_i = 0;
     double best_d = 0., best_s = 0., best_t = 0.;
     for (int k = 0; k < K; ++k) {
         const int i = idx[k];
@@ -268,7 +272,7 @@ __device__ void project_on_candidates(const RewardView& v, const int* idx, int K
         const double s_proj = v.s[i] + tp * sqrt(abx * abx + aby * aby);
         const double t_signed = (x - px) * v.nrm[2 * i] + (y - py) * v.nrm[2 * i + 1];
         const double dist = sqrt((x - px) * (x - px) + (y - py) * (y - py));
-        if (!have || dist < best_d) { have = true; best_d = dist; best_s = s_proj; best_t = t_signed; }
+        if (!have || dist < best_d) { have = true; best_d = dist; best_s = s_proj; best_t = t_signed; best_i = i; }
     }
     if (!have) {   // degenerate fallback :90-93: snap to the nearest node
         int j = 0;
@@ -279,18 +283,19 @@ __device__ void project_on_candidates(const RewardView& v, const int* idx, int K
             if (d < bd) { bd = d; j = i; }
         }
         s_out = v.s[j]; t_out = 0.0;
-        return;
+        return j;
     }
     s_out = best_s; t_out = best_t;
+    return best_i;
 }
 
-__device__ double signed_step(const RewardView& v, RewardState& r, int who, double x, double y, double s_curr, double s_prev) {
+__device__ double signed_step(const RewardView& v, RewardState& r, int who, double x, double y, double s_curr, double s_prev, int seg_hint) {
     double ds_geom = s_curr - s_prev;                                   // delta_s, track_progress.py:97-104
     if (v.p.closed) { if (ds_geom > 0.5 * v.L) ds_geom -= v.L; if (ds_geom < -0.5 * v.L) ds_geom += v.L; }
     if (!r.has_p_prev[who]) { r.has_p_prev[who] = 1; r.p_prev[who][0] = x; r.p_prev[who][1] = y; return 0.0; }
     const double dx = x - r.p_prev[who][0], dy = y - r.p_prev[who][1];
     r.p_prev[who][0] = x; r.p_prev[who][1] = y;
-    const int idx = seg_index_at_s(v, s_curr);
+    const int idx = seg_index_at_s(v, s_curr, seg_hint);
     const double ds_sign = dx * v.tan[2 * idx] + dy * v.tan[2 * idx + 1];
     return copysign(fabs(ds_geom), fabs(ds_sign) > 1e-6 ? ds_sign : ds_geom);
 }
@@ -314,6 +319,7 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_sel[4];                   // prefix, remaining rank, count<=, min>
     __shared__ float s_q[2];
+    __shared__ int s_seg[2];                        // segment each car was projected on (hint for the arclength lookups)
     RewardState& r = v.st[env];
 
     if (tid == 0) {
@@ -382,8 +388,8 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
         }
         block_topk(best, s_cand, s_knn[who]);
     }
-    if (tid == 0) project_on_candidates(v, s_knn[0], KNN, s_pose[0], s_pose[1], s_proj[0], s_proj[1]);
-    if (tid == 32) project_on_candidates(v, s_knn[1], KNN, s_pose[2], s_pose[3], s_proj[2], s_proj[3]);
+    if (tid == 0) s_seg[0] = project_on_candidates(v, s_knn[0], KNN, s_pose[0], s_pose[1], s_proj[0], s_proj[1]);
+    if (tid == 32) s_seg[1] = project_on_candidates(v, s_knn[1], KNN, s_pose[2], s_pose[3], s_proj[2], s_proj[3]);
 
     // ---- np.quantile(rng, wall_q) of the float32 lidar (rewards.py:335-339): radix select of the two order statistics
     if (s_flag[2]) {
@@ -460,8 +466,8 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
         // _Prog.update :129-167
         if (!r.has_s_prev[0]) { r.has_s_prev[0] = 1; r.s_prev[0] = e_s; }
         if (!r.has_s_prev[1]) { r.has_s_prev[1] = 1; r.s_prev[1] = o_s; }
-        double de = signed_step(v, r, 0, ex, ey, e_s, r.s_prev[0]);
-        double dop = signed_step(v, r, 1, ox, oy, o_s, r.s_prev[1]);
+        double de = signed_step(v, r, 0, ex, ey, e_s, r.s_prev[0], s_seg[0]);
+        double dop = signed_step(v, r, 1, ox, oy, o_s, r.s_prev[1], s_seg[1]);
         r.s_prev[0] = e_s; r.s_prev[1] = o_s;
         if (r.buf_n < 20) {
             r.buf_sum += de; r.buf_n += 1;
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
             lead = lead < -v.p.lead_clip ? -v.p.lead_clip : (lead > v.p.lead_clip ? v.p.lead_clip : lead);
             r_lead = v.p.w_rel_lead * (lead / v.p.lead_clip);
         }
-        const int idx = seg_index_at_s(v, e_s);                          // lateral :323-333
+        const int idx = seg_index_at_s(v, e_s, s_seg[0]);                // lateral :323-333
         double wR = v.p.default_half_width, wL = v.p.default_half_width;
         if (v.wR && v.wL) { wR = v.wR[idx]; wL = v.wL[idx]; }
         double w_eff = e_t >= 0.0 ? wL : wR;

@@ -1,2 +1,2 @@
-(timeout 900 python -m pytest tests -m gpu -x -q -k "host or env_api" 2>&1 | tail -3)
-for z in 0 1; do for c in 1 2; do F110_HOST_ZEROCOPY=$z python bench.py --steps 100 --warmup 10 --no-cpu-baseline --host-chunks $c 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('zerocopy',$z,'chunks',$c,'e2e %.3e'%d['e2e']['value'], '%.4f ms'%d['e2e']['ms_per_step'])"; done; done
+(timeout 900 python -m pytest tests -m gpu -x -q -s -k "shaped" 2>&1 | tail -4)
+python tools/gpu_exp/reward_probe.py
