@@ -53,6 +53,7 @@ class BatchSim(object):
         self.N, self.A, self.B = int(num_envs), int(num_agents), int(num_beams)
         self.params = dict(default_params() if params is None else params)
         self.timestep = float(timestep)
+        self.theta_dis = int(theta_dis)
         integ = getattr(integrator, 'value', integrator)
         cfg = _lib.F110Config(abi_version=_lib.F110_ABI_VERSION, device=self.device.index, num_envs=self.N,
                               num_agents=self.A, num_beams=self.B, theta_dis=theta_dis, integrator=int(integ),
@@ -89,10 +90,14 @@ class BatchSim(object):
     def set_tables(self, sines, cosines):
         s = np.ascontiguousarray(sines, np.float64)
         c = np.ascontiguousarray(cosines, np.float64)
+        if not (s.size == c.size == self.theta_dis):
+            raise ValueError("sin/cos tables must have theta_dis = %d entries" % self.theta_dis)
         _lib.check(self.lib.f110_set_tables(self.h, s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p)))
 
     def set_beam_tables(self, scan_angles, cosines, side_distances):
         a, c, s = (np.ascontiguousarray(v, np.float64) for v in (scan_angles, cosines, side_distances))
+        if not (a.size == c.size == s.size == self.B):
+            raise ValueError("beam tables must have num_beams = %d entries" % self.B)
         _lib.check(self.lib.f110_set_beam_tables(self.h, a.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
                                                  s.ctypes.data_as(C.c_void_p)))
 

@@ -34,7 +34,8 @@ class GpuBackend(object):
         self.sim = BatchSim(num_envs, num_agents, outputs=ALL_OUTPUTS, noise_std=kw.pop('noise_std', 0.0), **kw)
         s, c, a, bc, sd = H.tables()
         self.sim.set_tables(s, c)
-        self.sim.set_beam_tables(a, bc, sd)
+        if self.sim.B == len(a) and kw.get('fov', 4.7) == 4.7:     # the fixture tables are the reference's 1080 x 4.7 rad ones
+            self.sim.set_beam_tables(a, bc, sd)
         self.sim.set_map_arrays(*H.golden_map(map_name))
 
     def _np(self, o):
@@ -60,7 +61,8 @@ def make_oracle(num_envs, num_agents, map_name, **kw):
     o = Oracle(num_envs, num_agents, **kw)
     s, c, a, bc, sd = H.tables()
     o.set_tables(s, c)
-    o.set_beam_tables(a, bc, sd)
+    if o.B == len(a) and kw.get('fov', 4.7) == 4.7:
+        o.set_beam_tables(a, bc, sd)
     o.set_map_arrays(*H.golden_map(map_name))
     return o
 
@@ -539,3 +541,39 @@ def test_ros_bridge_call_pattern(tmp_path):
     obs, reward, terminated, truncated, info = env1.step(np.array([[0.0, 1.0]]))
     assert len(list(obs[0])) == 1080
     env.close(); env1.close()
+
+
+@pytest.mark.parametrize("num_envs,num_agents,num_beams,fov", [(5, 16, 1080, 4.7), (33, 6, 64, 3.0), (7, 4, 4320, 4.7), (1, 2, 32, 1.0)])
+def test_shape_extremes_vs_oracle(num_envs, num_agents, num_beams, fov):
+    """Edges of the supported shapes: the maximum agent count (one env per post-kernel CTA), the minimum beam count, a
+    non-default field of view, 4320 beams, ragged env counts -- each against the oracle with injected noise."""
+    from f110_gymnasium_ros2_jazzy_b200.params import beam_tables, default_params, theta_tables
+    rng = np.random.default_rng(1000 + num_agents)
+    be = GpuBackend(num_envs, num_agents, 'open_square', num_beams=num_beams, fov=fov)
+    orc = make_oracle(num_envs, num_agents, 'open_square', num_beams=num_beams, fov=fov)
+    # the fixture tables are for 1080 beams / 4.7 rad: rebuild them for this shape, identically on both sides
+    s, c = theta_tables(2000)
+    a, bc, sd = beam_tables(default_params(), num_beams, fov)
+    for x in (be.sim, orc):
+        x.set_tables(s, c)
+        x.set_beam_tables(a, bc, sd)
+    poses = np.zeros((num_envs, num_agents, 3))
+    poses[..., 0] = rng.uniform(-7, 7, size=(num_envs, num_agents))
+    poses[..., 1] = rng.uniform(-7, 7, size=(num_envs, num_agents))
+    poses[..., 2] = rng.uniform(-np.pi, np.pi, size=(num_envs, num_agents))
+    poses[:, 1, :2] = poses[:, 0, :2] + rng.uniform(-0.3, 0.3, size=(num_envs, 2))     # a guaranteed overlap per env
+    outl = beams = 0
+    for t in range(40):
+        noise = rng.normal(0, 0.01, size=(num_envs, num_agents, num_beams))
+        if t == 0:
+            g, o = be.reset(poses, noise), orc.reset(poses, noise)
+            assert g['collisions'][:, :2].all()          # the overlapping pair is flagged by GJK
+        else:
+            act = rng.uniform([-0.4189, 0], [0.4189, 6], size=(num_envs, num_agents, 2)).astype(np.float32)
+            g, o = be.step(act, noise), orc.step(act, noise)
+        for k in ('collisions', 'terminated', 'toggles'):
+            assert np.array_equal(g[k], o[k]), (k, t)
+        assert np.abs(g['state'] - o['state']).max() <= STATE_TOL
+        d = np.abs(g['scans'] - o['scans'])
+        outl += int((d > SCAN_TOL).sum()); beams += d.size
+    assert outl <= (1 - SCAN_FRAC) * beams
