@@ -271,6 +271,7 @@ class F110HostVecEnv(object):
             shape, dtype = _OUT_SPECS[key]
             self.out[key] = torch.zeros(shape(num_envs, num_agents, num_beams), dtype=dtype, pin_memory=True)
         self._views = [{key: t[self.bounds[k]:self.bounds[k + 1]] for key, t in self.out.items()} for k in range(chunks)]
+        self._np = {key: t.numpy() for key, t in self.out.items()}     # numpy views of the pinned outputs, made once
         self.start_poses = None
         self._term_t = torch.ones(num_envs, dtype=torch.uint8, pin_memory=True)
         self._term = self._term_t.numpy()
@@ -321,14 +322,14 @@ class F110HostVecEnv(object):
         self._term[:] = 1
         self._build_ios()
         o = self._run(None)
-        return o['obs'].numpy(), o
+        return self._np['obs'], o
 
     def step(self, actions):
         """actions: numpy (or pinned tensor viewed as numpy) [N, A, 2] f32/f64."""
         # the previous step's `terminated` (still in the pinned output buffer) is this step's reset mask
-        np.copyto(self._term, self.out['terminated'].numpy())
+        np.copyto(self._term, self._np['terminated'])
         o = self._run(actions)
-        return o['obs'].numpy(), o['reward'].numpy(), o['terminated'].numpy(), None, o
+        return self._np['obs'], self._np['reward'], self._np['terminated'], None, o
 
     def close(self):
         for b in self.parts:
