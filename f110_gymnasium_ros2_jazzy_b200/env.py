@@ -199,7 +199,8 @@ class F110VecEnv(object):
 
     def __init__(self, num_envs, map_dir=None, map=None, map_ext='.png', num_agents=2, params=None, seed=42,
                  timestep=0.01, ego_idx=0, integrator=Integrator.RK4, lidar_dist=0.0, device=None, auto_reset=True,
-                 outputs=FAST_OUTPUTS, noise_std=0.01, num_beams=1080, fov=4.7, count_lookups=False, map_arrays=None):
+                 outputs=FAST_OUTPUTS, noise_std=0.01, num_beams=1080, fov=4.7, count_lookups=False, map_arrays=None,
+                 cuda_graph=False):
         self.num_envs, self.num_agents = num_envs, num_agents
         self.timestep = timestep
         self.auto_reset = auto_reset
@@ -216,6 +217,11 @@ class F110VecEnv(object):
         self.truncated = torch.zeros(num_envs, dtype=torch.uint8, device=self.device)
         self.single_observation_shape = (num_beams + 8,)
         self.single_action_shape = (num_agents, 2)
+        # cuda_graph=True: the step (3-4 kernel launches) is captured once and replayed, one launch per step on the host side
+        self.cuda_graph = cuda_graph
+        self._graph = None
+        self._act = torch.zeros((num_envs, num_agents, 2), dtype=torch.float32, device=self.device)
+        self._steps_eager = 0
 
     def reset(self, poses, noise=None):
         """poses [N, A, 3] (or [A, 3], broadcast to every env)."""
@@ -223,11 +229,31 @@ class F110VecEnv(object):
         if p.ndim == 2:
             p = p[None].expand(self.num_envs, -1, -1)
         self.start_poses = p.to(self.device).contiguous()
+        self._graph = None          # the captured step holds the old start-pose tensor
+        self._steps_eager = 0
         o = self.backend.reset(self.start_poses, noise)
         return o['obs'], o
 
     def step(self, actions, noise=None):
         o = self.backend.out
+        if self.cuda_graph and noise is None and self.auto_reset and self.start_poses is not None:
+            self._act.copy_(torch.as_tensor(actions, device=self.device).reshape(self._act.shape))
+            if self._graph is None and self._steps_eager >= 1:
+                # capture on a side stream (the first step ran eagerly and warmed everything up); capture does not execute
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        self.backend.step(self._act, None, reset_mask=o['terminated'], reset_poses=self.start_poses)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._graph = g
+            if self._graph is not None:
+                self._graph.replay()
+                return o['obs'], o['reward'], o['terminated'], self.truncated, o
+            self._steps_eager += 1
+            o = self.backend.step(self._act, None, reset_mask=o['terminated'], reset_poses=self.start_poses)
+            return o['obs'], o['reward'], o['terminated'], self.truncated, o
         if self.auto_reset:
             # `terminated` of the previous step doubles as this step's reset mask (read by K1 before K3 rewrites it)
             o = self.backend.step(actions, noise, reset_mask=o['terminated'], reset_poses=self.start_poses)

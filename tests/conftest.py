@@ -13,6 +13,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: differential test against the live reference (build container only)")
 
 
+def pytest_sessionstart(session):
+    """Make sure the native artefacts exist (no-op when they are up to date): libf110_b200.so (nvcc cross-compiles without a
+    GPU) and the CPU oracle.  The GPU box receives the prebuilt files with the snapshot."""
+    import __graft_entry__
+    __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     from tests import helpers

@@ -577,3 +577,24 @@ def test_shape_extremes_vs_oracle(num_envs, num_agents, num_beams, fov):
         d = np.abs(g['scans'] - o['scans'])
         outl += int((d > SCAN_TOL).sum()); beams += d.size
     assert outl <= (1 - SCAN_FRAC) * beams
+
+
+def test_vec_env_cuda_graph_mode_matches_eager():
+    """F110VecEnv(cuda_graph=True): capture once, replay per step -- same results as the eager env (noise off)."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import F110VecEnv
+    N = 128
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
+    a = F110VecEnv(N, num_agents=1, map_arrays=m, noise_std=0.0)
+    b = F110VecEnv(N, num_agents=1, map_arrays=m, noise_std=0.0, cuda_graph=True)
+    a.reset(poses); b.reset(poses)
+    rng = np.random.default_rng(8)
+    for t in range(120):
+        act = torch.from_numpy(rng.uniform([-0.4189, 0], [0.4189, 18], size=(N, 1, 2)).astype(np.float32)).cuda()
+        oa = a.step(act); ob = b.step(act)
+        torch.cuda.synchronize()
+        assert torch.equal(oa[0], ob[0]) and torch.equal(oa[2], ob[2]), t
+    assert b._graph is not None
+    a.close(); b.close()
