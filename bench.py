@@ -310,6 +310,7 @@ def main():
         for k in range(W + min(K, 50)):
             cenv.step(acts[k])
         looks, rays = cenv.backend.lookup_count()
+        max_lookups = cenv.backend.max_lookups
         cenv.close()
         lbar = looks / max(rays, 1)
         bytes_per_ray = 8.0 * lbar + 8.0                      # L-bar fp64 cells + fp64 range out
@@ -323,7 +324,7 @@ def main():
         gather = gather_roofline(map_arrays[0], E * A * B, lbar, torch, dev)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
-                    "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar,
+                    "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar, "longest_ray_lookups": max_lookups,
                     "bytes_per_ray": bytes_per_ray, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                     "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]},
                     "gather_roofline": dict(gather, frac_of_whole_map=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["whole_map_gbs"],

@@ -263,6 +263,7 @@ class BatchSim(object):
     def lookup_count(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         _lib.check(self.lib.f110_get_lookup_count(self.h, C.byref(a), C.byref(b)))
+        self.max_lookups = int(self.lib.f110_max_lookups(self.h))
         return a.value, b.value
 
     @property

@@ -67,6 +67,7 @@ struct F110Sim {
     char* io_blob = nullptr; size_t io_bytes = 0;
     int64_t launches = 0;
     bool timing = false;
+    unsigned long long max_lookups = 0;   // longest ray (lookups) seen, refreshed by f110_get_lookup_count
     int lidar_threads = 128;
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
 };
@@ -89,7 +90,7 @@ void layout_scratch(Arena& a, StepScratch& sc, int NA, int B) {
     sc.scan_x = a.take<double>(NA); sc.scan_y = a.take<double>(NA); sc.pre_yaw = a.take<double>(NA);
     sc.theta0 = a.take<double>(NA);
     sc.ttc_hit = a.take<int32_t>(NA);
-    sc.lookups = a.take<unsigned long long>(2);
+    sc.lookups = a.take<unsigned long long>(4);
     sc.stats = a.take<double>(F110_NUM_STATS);
     sc.scan = a.take<double>((size_t)NA * B);
     sc.num_units = (unsigned)((((size_t)NA * B + 31) / 32 + 3) / 4 * 4);
@@ -484,9 +485,10 @@ int f110_get_lookup_count(F110Sim* sim, uint64_t* lookups, uint64_t* rays) {
     if (!sim->count_lookups) return fail(F110_ERR_INVALID, "handle was created without F110_FLAG_COUNT_LOOKUPS");
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
-    unsigned long long h[2];
+    unsigned long long h[3];
     CUDA_TRY(cudaMemcpy(h, sim->sc.lookups, sizeof(h), cudaMemcpyDeviceToHost));
     *lookups = h[0]; *rays = h[1];
+    sim->max_lookups = h[2];
     return F110_OK;
 }
 
@@ -513,6 +515,8 @@ int f110_get_kernel_timing(F110Sim* sim, double* ms3, int64_t* steps) {
     sim->tev.clear();
     return F110_OK;
 }
+
+int64_t f110_max_lookups(const F110Sim* sim) { return sim ? (int64_t)sim->max_lookups : 0; }
 
 int64_t f110_kernel_launches(const F110Sim* sim) { return sim ? sim->launches : 0; }
 

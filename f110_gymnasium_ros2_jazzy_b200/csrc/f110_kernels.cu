@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
         if (lane == 0 && wrays) {
             atomicAdd(sc.lookups, (unsigned long long)wsum);
             atomicAdd(sc.lookups + 1, (unsigned long long)wrays);
+            atomicMax(sc.lookups + 2, (unsigned long long)wmax);   // longest ray seen so far
         }
     }
 }

@@ -52,7 +52,7 @@ struct StepScratch {
     double* theta0;     // [NA] wrapped theta index of beam 0 (laser_models.py:167-172)
     int32_t* ttc_hit;   // [NA] set by the lidar kernel
     double* scan;       // [NA][B] noisy map scan, before the opponent ray-cast
-    unsigned long long* lookups;  // [2] dt lookups, rays (only with F110_FLAG_COUNT_LOOKUPS)
+    unsigned long long* lookups;  // [3] dt lookups, rays, longest ray (only with F110_FLAG_COUNT_LOOKUPS)
     double* stats;      // [F110_NUM_STATS]
     // launch-order history of the lidar kernel (see lidar_kernel): [0] = this step's order, [1] = being recorded
     unsigned num_units;        // ceil(NA*B / 32) warp-sized work units, padded to a multiple of 4

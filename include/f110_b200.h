@@ -177,6 +177,8 @@ int f110_get_stats(F110Sim* sim, double* out, int32_t reset, void* stream);
 
 /* Sum of distance-transform lookups since creation (requires F110_FLAG_COUNT_LOOKUPS); synchronises. */
 int f110_get_lookup_count(F110Sim* sim, uint64_t* lookups, uint64_t* rays);
+/* Longest ray (in lookups) seen so far, as of the last f110_get_lookup_count call. */
+int64_t f110_max_lookups(const F110Sim* sim);
 
 /* Per-kernel timing for bench.py's roofline: when enabled every f110_step records CUDA events around its three
  * kernels on the launch stream (not capturable into a CUDA graph while enabled).  f110_get_kernel_timing
