@@ -49,6 +49,9 @@ struct Arena {
 
 }  // namespace
 
+// records the message f110_last_error() returns (used by the other translation units of the library)
+int f110_set_error(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
+
 struct F110Sim {
     F110Config cfg;
     SimConst c;

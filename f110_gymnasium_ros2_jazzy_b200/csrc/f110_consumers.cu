@@ -13,6 +13,8 @@
 
 #include "f110_b200.h"
 
+int f110_set_error(int code, const char* msg);   // f110_capi.cu
+
 namespace {
 
 constexpr int GF_THREADS = 128;
@@ -138,12 +140,12 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
                                float* actions, int64_t action_stride, double angle_min, double angle_increment,
                                float max_distance, int32_t window_size, int32_t bubble_radius, float threshold, void* stream) {
     if (!scans || !actions || num_scans < 0 || num_beams < 1 || num_beams > 8192 || window_size < 1 || window_size > 15)
-        return F110_ERR_INVALID;
+        return f110_set_error(F110_ERR_INVALID, "f110_gap_follow: need non-null buffers, 1 <= num_beams <= 8192, 1 <= window_size <= 15");
     if (num_scans == 0) return F110_OK;
     gap_follow_kernel<<<(unsigned)num_scans, GF_THREADS, 2 * sizeof(float) * num_beams, (cudaStream_t)stream>>>(
         scans, scan_stride, num_beams, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
         bubble_radius, threshold);
-    return cudaPeekAtLastError() == cudaSuccess ? F110_OK : F110_ERR_CUDA;
+    return cudaPeekAtLastError() == cudaSuccess ? F110_OK : f110_set_error(F110_ERR_CUDA, "f110_gap_follow: kernel launch failed");
 }
 
 // =====================================================================================================================
@@ -535,9 +537,14 @@ __global__ void __launch_bounds__(RW_THREADS) shaped_reward_kernel(RewardView v,
 extern "C" int f110_reward_create(const F110RewardConfig* cfg, const double* xy, const double* wR, const double* wL,
                                   F110Reward** out) {
     if (!cfg || !xy || !out || cfg->num_envs < 1 || cfg->num_points < 2 || cfg->num_beams < 1 || cfg->num_beams > 8192)
-        return F110_ERR_INVALID;
+        return f110_set_error(F110_ERR_INVALID, "f110_reward_create: need num_envs >= 1, num_points >= 2, 1 <= num_beams <= 8192");
+    if ((cfg->num_points - 1 + MID_BLOCK - 1) / MID_BLOCK > 256)
+        return f110_set_error(F110_ERR_INVALID, "f110_reward_create: at most 16384 centerline points");
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return F110_ERR_NO_DEVICE; }
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return f110_set_error(F110_ERR_NO_DEVICE, "no CUDA device visible: libf110_b200 has no CPU fallback");
+    }
     int prev = 0;
     cudaGetDevice(&prev);
     if (cudaSetDevice(cfg->device) != cudaSuccess) return F110_ERR_CUDA;
@@ -592,7 +599,7 @@ extern "C" int f110_reward_create(const F110RewardConfig* cfg, const double* xy,
              cudaMemcpy(r->state, init.data(), sizeof(RewardState) * init.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     }
     cudaSetDevice(prev);
-    if (!ok) { f110_reward_destroy(r); return F110_ERR_CUDA; }
+    if (!ok) { f110_reward_destroy(r); cudaGetLastError(); return f110_set_error(F110_ERR_CUDA, "f110_reward_create: device allocation / upload failed"); }
     *out = r;
     return F110_OK;
 }
@@ -606,7 +613,7 @@ extern "C" void f110_reward_destroy(F110Reward* r) {
 
 extern "C" int f110_reward_compute(F110Reward* r, const float* obs, const uint8_t* reset_mask, double* out_f64, float* out_f32,
                                    void* stream) {
-    if (!r || !obs || (!out_f64 && !out_f32)) return F110_ERR_INVALID;
+    if (!r || !obs || (!out_f64 && !out_f32)) return f110_set_error(F110_ERR_INVALID, "f110_reward_compute: null handle, obs or outputs");
     RewardView v;
     v.p = r->cfg; v.n = r->n; v.L = r->L;
     v.blk = r->blk; v.nblk = r->nblk;

@@ -90,3 +90,4 @@ void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses
 
 // exact EDT on the device (f110_edt.cu): freemask DEVICE [H][W] (non-zero = free), dt DEVICE fp64 [H][W]; synchronises
 int edt_device(const uint8_t* freemask, int H, int W, double resolution, double* dt, cudaStream_t stream);
+int f110_set_error(int code, const char* msg);   // sets the thread-local message of f110_last_error(); returns code
