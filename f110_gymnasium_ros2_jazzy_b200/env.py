@@ -357,6 +357,34 @@ class F110HostVecEnv(object):
         o = self._run(actions)
         return self._np['obs'], self._np['reward'], self._np['terminated'], None, o
 
+    # ---- pipelined use (EnvPool-style): the chunks step independently, so the host can prepare chunk k's next
+    # actions while the other chunks' kernels and downloads are in flight ACROSS step boundaries.  Per chunk the
+    # order is recv(k) -> read chunk_out(k) -> send(k, actions); a chunk's buffers must not be touched between
+    # send and recv.
+    def chunk_slice(self, k):
+        return slice(self.bounds[k], self.bounds[k + 1])
+
+    def send(self, k, actions):
+        """Enqueue one step of chunk k (upload, kernels, download) and return at once.  actions: [n_k, A, 2]."""
+        lo, hi = self.bounds[k], self.bounds[k + 1]
+        np.copyto(self._term[lo:hi], self._np['terminated'][lo:hi])
+        a = np.ascontiguousarray(actions)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        assert a.size == (hi - lo) * self.num_agents * 2
+        io = self._ios[k]
+        io.actions = a.ctypes.data
+        io.actions_f64 = int(a.dtype == np.float64)
+        self._keep_k = getattr(self, '_keep_k', {})
+        self._keep_k[k] = a
+        self._lib.check(self._lib.load().f110_step_host_async(self.parts[k].h, self._ios[k]))
+
+    def recv(self, k):
+        """Wait for chunk k's step; returns (obs, reward, terminated) views of the pinned buffers for that chunk."""
+        self._lib.check(self._lib.load().f110_host_sync(self.parts[k].h))
+        sl = self.chunk_slice(k)
+        return self._np['obs'][sl], self._np['reward'][sl], self._np['terminated'][sl]
+
     def close(self):
         for b in self.parts:
             b.close()

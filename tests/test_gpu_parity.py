@@ -335,6 +335,50 @@ def test_host_vec_env_matches_device_vec_env():
     host.close(); dev.close()
 
 
+def test_host_vec_env_send_recv_pipeline():
+    """send/recv per chunk, with the chunks out of phase across step boundaries, gives every chunk exactly the
+    trajectory the synchronous step() gives it."""
+    _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv
+    N, K, T = 90, 3, 60
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
+    sync = F110HostVecEnv(N, chunks=K, map_arrays=m, num_agents=1, noise_std=0.01)
+    pipe = F110HostVecEnv(N, chunks=K, map_arrays=m, num_agents=1, noise_std=0.01)
+    sync.reset(poses); pipe.reset(poses)
+    acts = np.random.default_rng(5).uniform([-0.4189, 0], [0.4189, 20], size=(T, N, 1, 2)).astype(np.float32)
+    want = []
+    for t in range(T):
+        o, r, d, _, _ = sync.step(acts[t])
+        want.append((o.copy(), r.copy(), d.copy()))
+    # chunk k runs k steps ahead of chunk K-1: start them staggered, then recv/send round-robin
+    step_of = [0] * K
+    for k in range(K):
+        pipe.send(k, acts[0][pipe.chunk_slice(k)])
+    done = 0
+    while done < K:
+        done = 0
+        for k in range(K):
+            if step_of[k] >= T:
+                done += 1
+                continue
+            o, r, d = pipe.recv(k)
+            t = step_of[k]
+            sl = pipe.chunk_slice(k)
+            assert np.array_equal(o, want[t][0][sl]), (k, t)
+            assert np.array_equal(r, want[t][1][sl]) and np.array_equal(d, want[t][2][sl]), (k, t)
+            step_of[k] += 1
+            if step_of[k] < T:
+                pipe.send(k, acts[step_of[k]][sl])
+                if k == 0 and step_of[k] + 1 < T and step_of[k] % 7 == 0:      # let chunk 0 run ahead now and then
+                    o, r, d = pipe.recv(0)
+                    assert np.array_equal(o, want[step_of[0]][0][sl])
+                    step_of[0] += 1
+                    pipe.send(0, acts[step_of[0]][sl])
+    sync.close(); pipe.close()
+
+
 def test_step_is_cuda_graph_capturable():
     """f110_step neither allocates nor synchronises: a step can be captured and replayed by torch.cuda.graph."""
     torch = _torch()
