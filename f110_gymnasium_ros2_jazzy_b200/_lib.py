@@ -14,6 +14,7 @@ F110_NUM_PARAMS = 18
 F110_NUM_STATS = 8
 F110_MAX_AGENTS = 16
 F110_FLAG_COUNT_LOOKUPS = 1
+F110_FLAG_NARROW_FRACTION = 2
 
 F110_OK = 0
 F110_ERR_INVALID, F110_ERR_MAP_NOT_SET, F110_ERR_CUDA, F110_ERR_INDEX = -1, -2, -3, -4

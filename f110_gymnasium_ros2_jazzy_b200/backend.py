@@ -44,7 +44,7 @@ class BatchSim(object):
     def __init__(self, num_envs, num_agents=2, params=None, seed=42, timestep=0.01, integrator=RK4, ego_idx=0,
                  lidar_dist=0.0, num_beams=1080, fov=4.7, theta_dis=2000, eps=1e-4, max_range=30.0,
                  ttc_thresh=0.005, noise_std=0.01, device=None, outputs=ALL_OUTPUTS, count_lookups=False,
-                 host_stream_rank=0):
+                 host_stream_rank=0, narrow_fraction=False):
         if not torch.cuda.is_available():
             raise RuntimeError("f110_gymnasium_ros2_jazzy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -57,7 +57,8 @@ class BatchSim(object):
         integ = getattr(integrator, 'value', integrator)
         cfg = _lib.F110Config(abi_version=_lib.F110_ABI_VERSION, device=self.device.index, num_envs=self.N,
                               num_agents=self.A, num_beams=self.B, theta_dis=theta_dis, integrator=int(integ),
-                              ego_idx=int(ego_idx), flags=_lib.F110_FLAG_COUNT_LOOKUPS if count_lookups else 0,
+                              ego_idx=int(ego_idx), flags=(_lib.F110_FLAG_COUNT_LOOKUPS if count_lookups else 0) |
+                              (_lib.F110_FLAG_NARROW_FRACTION if narrow_fraction else 0),   # narrow_fraction: test hook
                               host_stream_rank=int(host_stream_rank),
                               fov=fov, eps=eps, max_range=max_range, timestep=timestep, lidar_dist=lidar_dist,
                               ttc_thresh=ttc_thresh, lidar_max=float(self.params.get('lidar_max', 30.0)),

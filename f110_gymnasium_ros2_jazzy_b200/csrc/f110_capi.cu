@@ -60,6 +60,7 @@ struct F110Sim {
     MapView map;
     bool map_set = false;
     bool count_lookups = false;
+    bool narrow_fraction = false;
     // device memory
     char* state_blob = nullptr;   size_t state_bytes = 0;    // checkpointable
     char* scratch_blob = nullptr; size_t scratch_bytes = 0;
@@ -179,6 +180,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->cfg = *cfg;
     const int N = cfg->num_envs, A = cfg->num_agents, B = cfg->num_beams, NA = N * A;
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
+    sim->narrow_fraction = (cfg->flags & F110_FLAG_NARROW_FRACTION) != 0;
     if (const char* e = getenv("F110_LIDAR_THREADS")) {   // tuning knob, multiple of 32 in [32, 256]
         const int t = atoi(e);
         if (t >= 32 && t <= 128 && t % 32 == 0) sim->lidar_threads = t;
@@ -260,6 +262,18 @@ void f110_destroy(F110Sim* sim) {
     delete sim;
 }
 
+// fixed-point format of the guarded fast cell index (dt_lookup): as many fraction bits as a 32-bit quotient leaves
+static void set_fixed_point(MapView& m, int width, int height, bool narrow) {
+    const unsigned big = (unsigned)(width > height ? width : height);
+    unsigned bits = 0;
+    while ((big >> bits) != 0u) ++bits;            // bit_length(max(W, H)) <= 16
+    m.fx_bits = 32u - bits > 24u ? 24u : 32u - bits;
+    if (narrow) m.fx_bits = 6u;                    // F110_FLAG_NARROW_FRACTION
+    m.fx_mask = (1u << m.fx_bits) - 1u;
+    m.inv_fx = (1.0 / m.res) * (double)(1u << m.fx_bits);
+    m.w_fx = (unsigned)width << m.fx_bits; m.h_fx = (unsigned)height << m.fx_bits;
+}
+
 int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
                  double orig_x, double orig_y, double orig_cos, double orig_sin) {
     if (!sim || !dt || height < 1 || width < 1 || !(resolution > 0)) return fail(F110_ERR_INVALID, "bad map arguments");
@@ -276,8 +290,7 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
     sim->d_map = d;
     MapView& m = sim->map;
     m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; m.inv16 = (1.0 / resolution) * 65536.0;
-    m.w16 = (unsigned)width << 16; m.h16 = (unsigned)height << 16;
+    m.res = resolution; set_fixed_point(m, width, height, sim->narrow_fraction);
     m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
     m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
     sim->map_set = true;
@@ -305,8 +318,7 @@ int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, i
     sim->d_map = d;
     MapView& m = sim->map;
     m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; m.inv16 = (1.0 / resolution) * 65536.0;
-    m.w16 = (unsigned)width << 16; m.h16 = (unsigned)height << 16;
+    m.res = resolution; set_fixed_point(m, width, height, sim->narrow_fraction);
     m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
     m.wres = width * resolution; m.hres = height * resolution;
     sim->map_set = true;

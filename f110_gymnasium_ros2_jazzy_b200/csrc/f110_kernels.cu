@@ -305,34 +305,31 @@ __device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double 
     return idx;
 }
 
-// Cell index without the two fp64 divisions.  q = x_rot * (2^16 / res) is the quotient in 2^-16 cell units
-// (fl(x*inv)*2^16 == fl(x*(inv*2^16)): scaling by a power of two commutes with rounding).  Its error against
-// the true quotient is < 2.3e-16 relative (< 1e-6 units for maps up to 2^16 cells wide), and the reference's own
-// rounded quotient is within half an ulp of the true one, so whenever the 16 fractional bits are at least one
-// unit away from both cell edges, trunc(q) >> 16 is exactly the reference's int(x_rot/res) and (q < W << 16) is
-// exactly its in-map test.  Everything else -- the 2/65536 of lookups next to a cell edge, the map border, negative
-// (converts to 0), NaN (0) and huge (0xFFFFFFFF) coordinates -- takes the exact path.
+// Cell index without the two fp64 divisions.  q = x_rot * (2^F / res) is the quotient in 2^-F cell units, F = m.fx_bits
+// (fl(x*inv)*2^F == fl(x*(inv*2^F)): scaling by a power of two commutes with rounding).  Its error against the true
+// quotient is < 2.3e-16 relative, i.e. < 1e-6 units since q < 2^32, and the reference's own rounded quotient is within
+// half an ulp of the true one, so whenever the F fractional bits are at least one unit away from both cell edges,
+// trunc(q) >> F is exactly the reference's int(x_rot/res) and (q < W << F) is exactly its in-map test.  Everything
+// else -- the 2/2^F of lookups next to a cell edge, the map border, negative (converts to 0), NaN (0) and huge
+// (0xFFFFFFFF) coordinates -- is not decided here: fast_cell returns false and the caller takes the exact path.
 template <bool IDENT>
-__device__ __forceinline__ double dt_lookup(const MapView& m, double x, double y) {
+__device__ __forceinline__ void map_frame(const MapView& m, double x, double y, double& x_rot, double& y_rot) {
     const double x_trans = x - m.ox;
     const double y_trans = y - m.oy;
-    double x_rot, y_rot;
     if (IDENT) {          // orig_c == 1, orig_s == 0: x*1 + y*0 == x and -x*0 + y*1 == y exactly
         x_rot = x_trans; y_rot = y_trans;
     } else {
         x_rot = x_trans * m.oc + y_trans * m.os;
         y_rot = -x_trans * m.os + y_trans * m.oc;
     }
-    const unsigned ux = __double2uint_rz(x_rot * m.inv16);
-    const unsigned uy = __double2uint_rz(y_rot * m.inv16);
-    // (f - 1) <= 65533  <=>  1 <= f <= 65534 for the 16-bit fraction f
-    int idx;
-    if (((ux & 0xFFFFu) - 1u) <= 0xFFFDu && ((uy & 0xFFFFu) - 1u) <= 0xFFFDu && ux < m.w16 && uy < m.h16) {
-        idx = (int)(uy >> 16) * m.W + (int)(ux >> 16);
-    } else {
-        idx = cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last);
-    }
-    return __ldg(m.dt + idx);
+}
+
+__device__ __forceinline__ bool fast_cell(const MapView& m, double x_rot, double y_rot, int& idx) {
+    const unsigned ux = __double2uint_rz(x_rot * m.inv_fx);
+    const unsigned uy = __double2uint_rz(y_rot * m.inv_fx);
+    idx = (int)(uy >> m.fx_bits) * m.W + (int)(ux >> m.fx_bits);
+    // (f - 1) <= mask - 2  <=>  1 <= f <= mask - 1 for the fraction f
+    return ((ux & m.fx_mask) - 1u) <= m.fx_mask - 2u && ((uy & m.fx_mask) - 1u) <= m.fx_mask - 2u && ux < m.w_fx && uy < m.h_fx;
 }
 
 // Philox2x32-10 (Salmon et al. 2011), counter-based: no per-ray generator state in HBM.  One call yields the
@@ -436,15 +433,34 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
         // trace_ray, laser_models.py:129-144
         double x = sc.scan_x[s], y = sc.scan_y[s];
         const double eps = c.eps, max_range = c.max_range;
-        double d = dt_lookup<IDENT>(m, x, y);
-        double total_d = d;
-        nlook = 1;
-        while (d > eps && total_d <= max_range) {
-            x += d * cs;
-            y += d * sn;
-            d = dt_lookup<IDENT>(m, x, y);
+        // The hot loop holds only the guarded fixed-point lookup and no call: a lookup that lands in the guard band
+        // leaves it for good and the ray is finished by the second loop, in the reference's own arithmetic (two IEEE
+        // divisions per lookup).  A call inside the hot loop costs 5 % of the kernel: everything live across it has to
+        // sit in callee-saved registers or be re-read, lookup after lookup, for a path 4 in 2^21 lookups take.
+        double x_rot, y_rot, d = 1.0, total_d = 0.0;
+        int idx;
+        map_frame<IDENT>(m, x, y, x_rot, y_rot);
+        bool fast = fast_cell(m, x_rot, y_rot, idx);
+        while (fast) {
+            d = __ldg(m.dt + idx);
             total_d += d;
             ++nlook;
+            if (!(d > eps && total_d <= max_range)) break;
+            x += d * cs;
+            y += d * sn;
+            map_frame<IDENT>(m, x, y, x_rot, y_rot);
+            fast = fast_cell(m, x_rot, y_rot, idx);
+        }
+        if (!fast) {
+            for (;;) {
+                d = __ldg(m.dt + cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last));
+                total_d += d;
+                ++nlook;
+                if (!(d > eps && total_d <= max_range)) break;
+                x += d * cs;
+                y += d * sn;
+                map_frame<IDENT>(m, x, y, x_rot, y_rot);
+            }
         }
         if (total_d > max_range) total_d = max_range;
 

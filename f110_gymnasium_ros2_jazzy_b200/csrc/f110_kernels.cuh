@@ -17,8 +17,10 @@ struct MapView {
     int H, W;
     int last;           // (H-1)*W + (W-1): the cell numba's negative-index wrap lands on
     double res;         // metres per cell
-    double inv16;       // 2^16 / res: quotient in 2^-16 cell units for the guarded fast cell index
-    unsigned w16, h16;  // W << 16, H << 16
+    double inv_fx;      // 2^fx_bits / res: quotient in 2^-fx_bits cell units for the guarded fast cell index
+    unsigned w_fx, h_fx;  // W << fx_bits, H << fx_bits
+    unsigned fx_bits;   // fraction bits: 32 - bit_length(max(W, H)), at most 24 (W << fx_bits must fit 32 bits)
+    unsigned fx_mask;   // (1 << fx_bits) - 1
     double ox, oy, oc, os;
     double wres, hres;  // W*res, H*res
 };

@@ -68,6 +68,8 @@ enum {
 
 /* flags for F110Config.flags */
 #define F110_FLAG_COUNT_LOOKUPS 1u /* count distance-transform lookups (for the roofline's L-bar) */
+#define F110_FLAG_NARROW_FRACTION 2u /* test hook: 6 fraction bits in the lidar kernel's fixed-point cell index, so that
+                                        3 % of lookups (instead of 1e-6) finish their ray on the exact-arithmetic path */
 
 typedef struct F110Sim F110Sim;
 

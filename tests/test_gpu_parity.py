@@ -91,6 +91,52 @@ def test_golden_scans_noise_free(map_name):
     assert (d <= SCAN_TOL).mean() >= SCAN_FRAC
 
 
+def _rotated_map_and_poses(theta, n=96):
+    """The Shanghai map under an origin with yaw theta (ScanSimulator2D.set_map keeps orig_c/orig_s, laser_models.py:421),
+    and centerline poses carried into that world frame."""
+    dt, res, o = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    cl = cl[np.linspace(0, len(cl) - 1, n).round().astype(int)]
+    o2 = [3.5, -7.25, theta]
+    mx, my = cl[:, 0] - o[0], cl[:, 1] - o[1]                    # map-frame coordinates
+    c, s = np.cos(theta), np.sin(theta)
+    poses = np.stack([o2[0] + c * mx - s * my, o2[1] + s * mx + c * my, cl[:, 2] + theta], axis=1)
+    return (dt, res, o2), poses
+
+
+@pytest.mark.parametrize('theta', [0.0, 0.3])
+def test_exact_finishing_path_scans(theta):
+    """F110_FLAG_NARROW_FRACTION leaves the fixed-point cell index 6 fraction bits, so about 6 % of lookups fall in the
+    guard band and their rays are finished by the lidar kernel's exact-arithmetic loop (normally 1e-6 of lookups).
+    The scans must not change by a bit, and must equal the oracle's -- on an axis-aligned and on a rotated map origin."""
+    from oracle.f110_oracle import Oracle
+    _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+    m, poses = _rotated_map_and_poses(theta)
+    n = len(poses)
+    orc = Oracle(1, 1); orc.set_map_arrays(*m)
+    s, c, _, _, _ = H.tables()
+    orc.set_tables(s, c)
+    want = np.stack([orc.scan(p)[0] for p in poses])
+    outs = []
+    for narrow in (False, True):
+        sim = BatchSim(n, 1, outputs=ALL_OUTPUTS, noise_std=0.0, narrow_fraction=narrow)
+        sim.set_tables(s, c)
+        sim.set_map_arrays(*m)
+        sim.sim_reset(poses[:, None, :])
+        o = sim.step(None, np.zeros((n, 1, 1080)))
+        import torch
+        torch.cuda.synchronize()
+        outs.append(o['scans_f64'].cpu().numpy()[:, 0])
+        sim.close()
+    assert np.array_equal(outs[0], outs[1])
+    d = np.abs(outs[1] - want)
+    print('theta', theta, 'max', d.max(), 'exact fraction', float((d == 0).mean()))
+    assert (d <= SCAN_TOL).mean() >= SCAN_FRAC
+    if theta == 0.0:
+        assert d.max() == 0.0
+
+
 def test_c1_single_agent_sim_rollout():
     g = H.load('rollout_c1_single')
     be = make_gpu(1, 'Shanghai_map')
