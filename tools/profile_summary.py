@@ -61,8 +61,8 @@ def kernel(rep, name=None):
             vals = [r[i] for r in sel]
             print("%-70s %-12s %s" % (k, units[i], ' '.join(vals)))
             out[k] = (units[i], vals)
-    src = subprocess.check_output(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
-                                  stderr=subprocess.DEVNULL).decode()
+    src = subprocess.check_output(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'] +
+                                  (['-k', 'regex:' + name] if name else []), stderr=subprocess.DEVNULL).decode()
     rows = list(csv.reader(io.StringIO(src)))
     hdr = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
