@@ -388,60 +388,78 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream) {
     return run_step(sim, *io, (cudaStream_t)stream);
 }
 
+namespace {
+// One host<->device transfer of the host path.  The device mirrors of the fields present in a call are packed back to
+// back in io_blob in a fixed order (see f110_step_host_async), so transfers whose HOST buffers are also exactly adjacent,
+// in that order, travel as one cudaMemcpyAsync: a caller that carves its pinned buffers out of one block per direction
+// (F110HostVecEnv does) pays one PCIe transaction each way per step instead of one per field.
+struct Xfer { char* host; char* dev; size_t bytes; };
+
+int run_xfers(const Xfer* x, int n, cudaMemcpyKind kind, cudaStream_t s) {
+    for (int i = 0; i < n;) {
+        size_t bytes = x[i].bytes;
+        int j = i + 1;
+        while (j < n && x[j].host == x[i].host + bytes && x[j].dev == x[i].dev + bytes) bytes += x[j++].bytes;
+        if (kind == cudaMemcpyHostToDevice) CUDA_TRY(cudaMemcpyAsync(x[i].dev, x[i].host, bytes, kind, s));
+        else CUDA_TRY(cudaMemcpyAsync(x[i].host, x[i].dev, bytes, kind, s));
+        i = j;
+    }
+    return F110_OK;
+}
+}  // namespace
+
 int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     const int rc = check_step_io(sim, hio);
     if (rc != F110_OK) return rc;
     Guard g(sim->cfg.device);
     const size_t N = sim->c.N, NA = sim->c.NA, B = sim->c.B;
     if (!sim->io_blob) {
-        // device mirrors of every field of F110StepIO (worst case), allocated on first use
-        Arena m;
-        m.take<double>(NA * 2); m.take<double>(NA * B); m.take<uint8_t>(N); m.take<double>(NA * 3); m.take<uint8_t>(N);
-        m.take<float>(N * (B + 8)); m.take<float>(N); m.take<uint8_t>(N); m.take<double>(NA * B); m.take<float>(NA * B);
-        m.take<double>(NA * 7); m.take<uint8_t>(NA); m.take<int32_t>(NA); m.take<double>(NA); m.take<double>(NA); m.take<double>(N);
-        sim->io_bytes = (m.used + 255) & ~size_t(255);
+        // room for the device mirror of every field of F110StepIO at once, allocated on first use
+        sim->io_bytes = NA * 2 * 8 + NA * B * 8 + N + NA * 3 * 8 + N                       // inputs
+                      + N * (B + 8) * 4 + N * 4 + N + NA * B * 8 + NA * B * 4 + NA * 7 * 8  // outputs
+                      + NA + NA * 4 + NA * 8 + NA * 8 + N * 8 + 4096;
         CUDA_TRY(cudaMalloc(&sim->io_blob, sim->io_bytes));
     }
-    Arena a; a.base = sim->io_blob;
-    double* d_act = a.take<double>(NA * 2); double* d_noise = a.take<double>(NA * B); uint8_t* d_rmask = a.take<uint8_t>(N);
-    double* d_rposes = a.take<double>(NA * 3); uint8_t* d_amask = a.take<uint8_t>(N);
-    float* d_obs = a.take<float>(N * (B + 8)); float* d_rew = a.take<float>(N); uint8_t* d_term = a.take<uint8_t>(N);
-    double* d_s64 = a.take<double>(NA * B); float* d_s32 = a.take<float>(NA * B); double* d_state = a.take<double>(NA * 7);
-    uint8_t* d_col = a.take<uint8_t>(NA); int32_t* d_tog = a.take<int32_t>(NA); double* d_lt = a.take<double>(NA);
-    double* d_lc = a.take<double>(NA); double* d_time = a.take<double>(N);
-
     cudaStream_t s = sim->host_stream;
     F110StepIO d = *hio;
-#define H2D(field, dptr, bytes)                                                                   \
-    if (hio->field) { CUDA_TRY(cudaMemcpyAsync(dptr, hio->field, bytes, cudaMemcpyHostToDevice, s)); d.field = dptr; }
-    H2D(actions, d_act, NA * 2 * (hio->actions_f64 ? sizeof(double) : sizeof(float)))
-    H2D(noise, d_noise, NA * B * sizeof(double))
-    H2D(reset_mask, d_rmask, N)
-    H2D(reset_poses, d_rposes, NA * 3 * sizeof(double))
-    H2D(active_mask, d_amask, N)
-#undef H2D
-    d.obs = hio->obs ? d_obs : nullptr; d.reward = hio->reward ? d_rew : nullptr; d.terminated = hio->terminated ? d_term : nullptr;
-    d.scans_f64 = hio->scans_f64 ? d_s64 : nullptr; d.scans_f32 = hio->scans_f32 ? d_s32 : nullptr;
-    d.state = hio->state ? d_state : nullptr; d.collisions = hio->collisions ? d_col : nullptr;
-    d.toggles = hio->toggles ? d_tog : nullptr; d.lap_times = hio->lap_times ? d_lt : nullptr;
-    d.lap_counts = hio->lap_counts ? d_lc : nullptr; d.time = hio->time ? d_time : nullptr;
-    const int rc2 = run_step(sim, d, s);
+    Xfer in[5], out[11];
+    int n_in = 0, n_out = 0;
+    char* cur = sim->io_blob;
+    // field present in the caller's struct -> next slot of io_blob; the device-side struct points there
+#define SLOT(list, count, field, nbytes)                                                           \
+    if (hio->field) {                                                                              \
+        list[count++] = Xfer{(char*)(uintptr_t)hio->field, cur, (size_t)(nbytes)};                 \
+        d.field = (decltype(d.field))cur;                                                          \
+        cur += (nbytes);                                                                           \
+    }
+    // inputs, in merge order: actions, reset_poses, noise (8-byte multiples), reset_mask, active_mask (bytes)
+    SLOT(in, n_in, actions, NA * 2 * (hio->actions_f64 ? sizeof(double) : sizeof(float)))
+    SLOT(in, n_in, reset_poses, NA * 3 * sizeof(double))
+    SLOT(in, n_in, noise, NA * B * sizeof(double))
+    SLOT(in, n_in, reset_mask, N)
+    SLOT(in, n_in, active_mask, N)
+    cur = sim->io_blob + (((size_t)(cur - sim->io_blob) + 255) & ~size_t(255));
+    // outputs, in merge order: obs, scans_f32, reward (f32), toggles (i32) | scans_f64, state, lap_times, lap_counts,
+    // time (f64) | terminated, collisions (bytes).  The 4-byte group holds an even number of words whenever the f64
+    // group follows a complete one (N * (B + 8) + N is even for even N); otherwise one pad word keeps f64 aligned.
+    SLOT(out, n_out, obs, N * (B + 8) * sizeof(float))
+    SLOT(out, n_out, scans_f32, NA * B * sizeof(float))
+    SLOT(out, n_out, reward, N * sizeof(float))
+    SLOT(out, n_out, toggles, NA * sizeof(int32_t))
+    cur = sim->io_blob + (((size_t)(cur - sim->io_blob) + 7) & ~size_t(7));
+    SLOT(out, n_out, scans_f64, NA * B * sizeof(double))
+    SLOT(out, n_out, state, NA * 7 * sizeof(double))
+    SLOT(out, n_out, lap_times, NA * sizeof(double))
+    SLOT(out, n_out, lap_counts, NA * sizeof(double))
+    SLOT(out, n_out, time, N * sizeof(double))
+    SLOT(out, n_out, terminated, N)
+    SLOT(out, n_out, collisions, NA)
+#undef SLOT
+    int rc2 = run_xfers(in, n_in, cudaMemcpyHostToDevice, s);
     if (rc2 != F110_OK) return rc2;
-#define D2H(field, dptr, bytes) \
-    if (hio->field) CUDA_TRY(cudaMemcpyAsync(hio->field, dptr, bytes, cudaMemcpyDeviceToHost, s));
-    D2H(obs, d_obs, N * (B + 8) * sizeof(float))
-    D2H(reward, d_rew, N * sizeof(float))
-    D2H(terminated, d_term, N)
-    D2H(scans_f64, d_s64, NA * B * sizeof(double))
-    D2H(scans_f32, d_s32, NA * B * sizeof(float))
-    D2H(state, d_state, NA * 7 * sizeof(double))
-    D2H(collisions, d_col, NA)
-    D2H(toggles, d_tog, NA * sizeof(int32_t))
-    D2H(lap_times, d_lt, NA * sizeof(double))
-    D2H(lap_counts, d_lc, NA * sizeof(double))
-    D2H(time, d_time, N * sizeof(double))
-#undef D2H
-    return F110_OK;
+    rc2 = run_step(sim, d, s);
+    if (rc2 != F110_OK) return rc2;
+    return run_xfers(out, n_out, cudaMemcpyDeviceToHost, s);
 }
 
 int f110_host_sync(F110Sim* sim) {

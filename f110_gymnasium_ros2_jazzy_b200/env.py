@@ -270,16 +270,25 @@ class F110HostVecEnv(object):
 
     This is the end-to-end shape of the reference's own use (train_ddpg.py:160-202 reads the observation on the
     host every step).  The envs are split over ``chunks`` independent library handles, each with its own stream;
-    a step enqueues, per chunk, the action upload, the three kernels and the observation download
-    (f110_step_host_async), then waits for all of them (f110_host_sync) -- so one chunk's PCIe traffic overlaps
-    the other chunks' kernels.  Auto-reset as in F110VecEnv.
+    a step enqueues, per chunk, the upload, the three kernels and the downloads (f110_step_host_async), then waits
+    for all of them (f110_host_sync) -- so one chunk's PCIe traffic overlaps the other chunks' kernels.  Per chunk the
+    inputs (actions, start poses, reset mask) sit back to back in one pinned block and so do reward and terminated,
+    which the library then moves with one copy each (include/f110_b200.h, f110_step_host_async); the observation
+    goes straight into its slice of one contiguous [N, B+8] pinned array.  Auto-reset as in F110VecEnv.
+
+    ``chunks``: an int (equal chunks) or relative sizes, e.g. (1, 3): a small first chunk starts the downloads sooner.
     """
 
     def __init__(self, num_envs, chunks=2, map_arrays=None, map_dir=None, map=None, map_ext='.png', num_agents=1,
                  seed=42, device=None, outputs=FAST_OUTPUTS, num_beams=1080, **kw):
-        chunks = max(1, min(chunks, num_envs))
         self.num_envs, self.num_agents, self.num_beams = num_envs, num_agents, num_beams
-        self.bounds = [(num_envs * k) // chunks for k in range(chunks + 1)]
+        if isinstance(chunks, int):
+            chunks = max(1, min(chunks, num_envs))
+            self.bounds = [(num_envs * k) // chunks for k in range(chunks + 1)]
+        else:
+            w = np.cumsum([0.0] + [float(v) for v in chunks])
+            self.bounds = sorted(set(int(round(num_envs * v / w[-1])) for v in w))
+            chunks = len(self.bounds) - 1
         self.parts = []
         for k in range(chunks):
             n = self.bounds[k + 1] - self.bounds[k]
@@ -291,69 +300,110 @@ class F110HostVecEnv(object):
                 b.set_map(map_dir + map + '.yaml', map_ext)
             self.parts.append(b)
         outs = tuple(dict.fromkeys(tuple(outputs) + ('obs', 'reward', 'terminated')))
-        self.out = {}
         from .backend import _OUT_SPECS
+        # whole-batch outputs.  reward / terminated are plain arrays gathered from the per-chunk blocks after a step;
+        # everything else is pinned and written by the copy engine directly
+        self.out, self._np = {}, {}
         for key in outs:
             shape, dtype = _OUT_SPECS[key]
-            self.out[key] = torch.zeros(shape(num_envs, num_agents, num_beams), dtype=dtype, pin_memory=True)
-        self._views = [{key: t[self.bounds[k]:self.bounds[k + 1]] for key, t in self.out.items()} for k in range(chunks)]
-        self._np = {key: t.numpy() for key, t in self.out.items()}     # numpy views of the pinned outputs, made once
+            if key in ('reward', 'terminated'):
+                self._np[key] = np.zeros(shape(num_envs, num_agents, num_beams), dtype=torch.zeros(0, dtype=dtype).numpy().dtype)
+                self.out[key] = torch.from_numpy(self._np[key])
+            else:
+                self.out[key] = torch.zeros(shape(num_envs, num_agents, num_beams), dtype=dtype, pin_memory=True)
+                self._np[key] = self.out[key].numpy()
+        self._np['terminated'][:] = 1
+        # per chunk: [reward f32 | terminated u8] in one pinned block
+        self._small, self._rew_k, self._term_k = [], [], []
+        for k in range(chunks):
+            n = self.bounds[k + 1] - self.bounds[k]
+            blk = torch.zeros(5 * n, dtype=torch.uint8, pin_memory=True)
+            self._small.append(blk)
+            self._rew_k.append(blk[:4 * n].view(torch.float32).numpy())
+            self._term_k.append(blk[4 * n:].numpy())
+        self._in = {}            # action dtype -> per-chunk input blocks (built at the first step with that dtype)
         self.start_poses = None
-        self._term_t = torch.ones(num_envs, dtype=torch.uint8, pin_memory=True)
-        self._term = self._term_t.numpy()
 
-    def _build_ios(self):
-        """The F110StepIO of every chunk, built once: all buffers are persistent (pinned outputs, reset mask, start
-        poses); only the action pointer changes from step to step."""
+    def _input_blocks(self, dtype):
+        """Per chunk one pinned block [actions | start poses f64 | reset mask u8] for actions of this dtype, and the
+        F110StepIO of every chunk pointing into it: all buffers are persistent, a step only fills them."""
         import ctypes as C
         from . import _lib
-        K = len(self.parts)
-        self._ios = (_lib.F110StepIO * K)()
-        self._handles = (C.c_void_p * K)(*[b.h for b in self.parts])
+        if dtype in self._in:
+            return self._in[dtype]
+        K, A = len(self.parts), self.num_agents
+        ios = (_lib.F110StepIO * K)()
+        acts, masks, keep = [], [], []
         for k in range(K):
-            lo = self.bounds[k]
-            io = self._ios[k]
-            io.reset_mask = self._term_t.data_ptr() + lo
-            io.reset_poses = self._poses_t.data_ptr() + lo * self.num_agents * 3 * 8
-            for key, t in self._views[k].items():
-                setattr(io, key, t.data_ptr())
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            n = hi - lo
+            ab = n * A * 2 * dtype.itemsize
+            blk = torch.zeros(ab + n * A * 24 + n, dtype=torch.uint8, pin_memory=True)
+            a = blk[:ab].numpy().view(dtype).reshape(n, A, 2)
+            p = blk[ab:ab + n * A * 24].numpy().view(np.float64).reshape(n, A, 3)
+            p[...] = self.start_poses[lo:hi]
+            m = blk[ab + n * A * 24:].numpy()
+            io = ios[k]
+            io.actions, io.actions_f64 = a.ctypes.data, int(dtype == np.float64)
+            io.reset_poses, io.reset_mask = p.ctypes.data, m.ctypes.data
+            io.reward, io.terminated = self._rew_k[k].ctypes.data, self._term_k[k].ctypes.data
+            for key, t in self.out.items():
+                if key not in ('reward', 'terminated'):
+                    setattr(io, key, t[lo:hi].data_ptr())
+            acts.append(a); masks.append(m); keep.append(blk)
+        handles = (C.c_void_p * K)(*[b.h for b in self.parts])
+        self._in[dtype] = (ios, handles, acts, masks, keep)
         self._lib = _lib
+        return self._in[dtype]
+
+    def _fill(self, k, blocks, actions):
+        """chunk k's inputs for the next step: its actions (None = zero action: a reset step) and, as reset mask, the
+        `terminated` its previous step produced."""
+        ios, _, acts, masks, _ = blocks
+        np.copyto(masks[k], self._term_k[k])
+        if actions is None:
+            ios[k].actions = None
+        else:
+            ios[k].actions = acts[k].ctypes.data
+            np.copyto(acts[k], actions.reshape(acts[k].shape))
+
+    def _gather(self, k):
+        sl = slice(self.bounds[k], self.bounds[k + 1])
+        self._np['reward'][sl] = self._rew_k[k]
+        self._np['terminated'][sl] = self._term_k[k]
+
+    @staticmethod
+    def _as_actions(actions):
+        a = np.asarray(actions)
+        return a if a.dtype in (np.float32, np.float64) else a.astype(np.float64)
 
     def _run(self, actions):
         K = len(self.parts)
-        if actions is None:
-            for k in range(K):
-                self._ios[k].actions = None
-        else:
-            a = np.ascontiguousarray(actions)
-            if a.dtype not in (np.float32, np.float64):
-                a = a.astype(np.float64)
+        a = None if actions is None else self._as_actions(actions)
+        blocks = self._input_blocks(np.dtype(np.float32) if a is None else a.dtype)
+        if a is not None:
             assert a.size == self.num_envs * self.num_agents * 2
-            item = a.dtype.itemsize * self.num_agents * 2
-            base = a.ctypes.data
-            f64 = int(a.dtype == np.float64)
-            for k in range(K):
-                self._ios[k].actions = base + self.bounds[k] * item
-                self._ios[k].actions_f64 = f64
-            self._keep = a
-        self._lib.check(self._lib.load().f110_step_host_multi(self._handles, self._ios, K))
+            a = a.reshape(self.num_envs, self.num_agents, 2)
+        for k in range(K):
+            self._fill(k, blocks, None if a is None else a[self.bounds[k]:self.bounds[k + 1]])
+        self._lib.check(self._lib.load().f110_step_host_multi(blocks[1], blocks[0], K))
+        for k in range(K):
+            self._gather(k)
         return self.out
 
     def reset(self, poses):
         p = np.asarray(poses, np.float64)
         if p.ndim == 2:
             p = np.broadcast_to(p[None], (self.num_envs,) + p.shape)
-        self._poses_t = torch.from_numpy(np.ascontiguousarray(p)).pin_memory()
-        self.start_poses = self._poses_t.numpy()
-        self._term[:] = 1
-        self._build_ios()
+        self.start_poses = np.ascontiguousarray(p)
+        self._in = {}
+        for t in self._term_k:
+            t[:] = 1
         o = self._run(None)
         return self._np['obs'], o
 
     def step(self, actions):
-        """actions: numpy (or pinned tensor viewed as numpy) [N, A, 2] f32/f64."""
-        # the previous step's `terminated` (still in the pinned output buffer) is this step's reset mask
-        np.copyto(self._term, self._np['terminated'])
+        """actions: numpy [N, A, 2] f32/f64.  The previous step's `terminated` is this step's reset mask."""
         o = self._run(actions)
         return self._np['obs'], self._np['reward'], self._np['terminated'], None, o
 
@@ -365,25 +415,17 @@ class F110HostVecEnv(object):
         return slice(self.bounds[k], self.bounds[k + 1])
 
     def send(self, k, actions):
-        """Enqueue one step of chunk k (upload, kernels, download) and return at once.  actions: [n_k, A, 2]."""
-        lo, hi = self.bounds[k], self.bounds[k + 1]
-        np.copyto(self._term[lo:hi], self._np['terminated'][lo:hi])
-        a = np.ascontiguousarray(actions)
-        if a.dtype not in (np.float32, np.float64):
-            a = a.astype(np.float64)
-        assert a.size == (hi - lo) * self.num_agents * 2
-        io = self._ios[k]
-        io.actions = a.ctypes.data
-        io.actions_f64 = int(a.dtype == np.float64)
-        self._keep_k = getattr(self, '_keep_k', {})
-        self._keep_k[k] = a
-        self._lib.check(self._lib.load().f110_step_host_async(self.parts[k].h, self._ios[k]))
+        """Enqueue one step of chunk k (upload, kernels, downloads) and return at once.  actions: [n_k, A, 2]."""
+        a = self._as_actions(actions)
+        blocks = self._input_blocks(a.dtype)
+        assert a.size == (self.bounds[k + 1] - self.bounds[k]) * self.num_agents * 2
+        self._fill(k, blocks, a)
+        self._lib.check(self._lib.load().f110_step_host_async(self.parts[k].h, blocks[0][k]))
 
     def recv(self, k):
         """Wait for chunk k's step; returns (obs, reward, terminated) views of the pinned buffers for that chunk."""
         self._lib.check(self._lib.load().f110_host_sync(self.parts[k].h))
-        sl = self.chunk_slice(k)
-        return self._np['obs'][sl], self._np['reward'][sl], self._np['terminated'][sl]
+        return self._np['obs'][self.chunk_slice(k)], self._rew_k[k], self._term_k[k]
 
     def close(self):
         for b in self.parts:

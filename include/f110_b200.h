@@ -103,7 +103,7 @@ typedef struct F110StepIO {
     int32_t reserved0;
     const double* noise;         /* [N][A][B] additive lidar noise drawn by the caller (parity mode: numpy's
                                     Generator.normal stream, laser_models.py:450-452); NULL = on-device
-                                    Philox4x32-10 + Box-Muller N(0, noise_std^2) */
+                                    Philox2x32-10 + Box-Muller N(0, noise_std^2) */
     const uint8_t* reset_mask;   /* [N] or NULL.  Non-zero: F110Env.reset(options=reset_poses[env]) is applied to the
                                     env first and this step is its zero-action step (f110_env.py:438-458); the env's
                                     action is ignored.  May alias `terminated` (auto-reset on the step after done). */
@@ -158,7 +158,11 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream);
 /* Same contract with HOST pointers in `io`; copies in and out on an internal stream and synchronises it. */
 int f110_step_host(F110Sim* sim, const F110StepIO* io);
 /* The same without the final synchronisation: the host buffers are valid after f110_host_sync().  Lets a caller
- * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels. */
+ * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels.
+ * Fields whose host buffers lie exactly back to back in the order
+ *     inputs : actions, reset_poses, noise, reset_mask, active_mask
+ *     outputs: obs, scans_f32, reward, toggles, scans_f64, state, lap_times, lap_counts, time, terminated, collisions
+ * (absent fields skipped) are moved by a single copy per direction; any other placement works, one copy per field. */
 int f110_step_host_async(F110Sim* sim, const F110StepIO* io);
 int f110_host_sync(F110Sim* sim);
 /* f110_step_host_async on `count` handles (ios[i] belongs to sims[i]), then f110_host_sync on each: one call per step
