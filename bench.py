@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--host-chunks", type=int, default=2, help="env chunks pipelined by the e2e host path")
+    ap.add_argument("--host-chunks", default="1,3", help="env chunks pipelined by the e2e host path: a count, or relative sizes "
+                    "(a small first chunk starts the downloads sooner)")
     ap.add_argument("--pipe-chunks", type=int, default=4, help="env chunks of the e2e send/recv (cross-step pipelined) figure")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     return ap.parse_args()
@@ -296,7 +297,7 @@ def main():
             el, el_pipe = float(t[0].item()), float(t[1].item())
         e2e = {"value": total_envs * K / el, "unit": "env-steps/s", "h2d_bytes_per_step": E * A * 2 * 4 + E + E * A * 3 * 8,
                "d2h_bytes_per_step": E * (B + 8) * 4 + E * 4 + E, "ms_per_step": 1e3 * el / K, "n_gpus": world,
-               "api": "F110HostVecEnv.step -> f110_step_host_async + f110_host_sync (C ABI, pinned host buffers, %d chunks)" % args.host_chunks,
+               "api": "F110HostVecEnv.step -> f110_step_host_async + f110_host_sync (C ABI, pinned host buffers, env chunks %s)" % args.host_chunks,
                "bytes_are": "per GPU",
                "pipelined": {"value": total_envs * K / el_pipe, "ms_per_step": 1e3 * el_pipe / K,
                              "chunks": args.pipe_chunks,
@@ -387,8 +388,9 @@ def e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch):
     downloads observation / reward / terminated into pinned host memory, inside the timed region (wall clock
     around K synchronous steps).  Returns elapsed seconds."""
     from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv
-    henv = F110HostVecEnv(E, chunks=args.host_chunks, map_arrays=map_arrays, num_agents=A, num_beams=B, device=local,
-                          noise_std=0.01)
+    hc = [int(v) for v in str(args.host_chunks).split(",")]
+    henv = F110HostVecEnv(E, chunks=hc[0] if len(hc) == 1 else tuple(hc), map_arrays=map_arrays, num_agents=A, num_beams=B,
+                          device=local, noise_std=0.01)
     hacts = acts.cpu().pin_memory().numpy()
     henv.reset(poses)
     for k in range(min(W, 5)):

@@ -15,6 +15,7 @@ F110_NUM_STATS = 8
 F110_MAX_AGENTS = 16
 F110_FLAG_COUNT_LOOKUPS = 1
 F110_FLAG_NARROW_FRACTION = 2
+F110_HOST_MERGE_ADJACENT = 1
 
 F110_OK = 0
 F110_ERR_INVALID, F110_ERR_MAP_NOT_SET, F110_ERR_CUDA, F110_ERR_INDEX = -1, -2, -3, -4
@@ -38,7 +39,7 @@ class F110Config(C.Structure):
 
 
 class F110StepIO(C.Structure):
-    _fields_ = [("actions", C.c_void_p), ("actions_f64", C.c_int32), ("reserved0", C.c_int32),
+    _fields_ = [("actions", C.c_void_p), ("actions_f64", C.c_int32), ("host_flags", C.c_int32),
                 ("noise", C.c_void_p), ("reset_mask", C.c_void_p), ("reset_poses", C.c_void_p),
                 ("active_mask", C.c_void_p),
                 ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("scans_f64", C.c_void_p),

@@ -391,15 +391,15 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream) {
 namespace {
 // One host<->device transfer of the host path.  The device mirrors of the fields present in a call are packed back to
 // back in io_blob in a fixed order (see f110_step_host_async), so transfers whose HOST buffers are also exactly adjacent,
-// in that order, travel as one cudaMemcpyAsync: a caller that carves its pinned buffers out of one block per direction
+// in that order, travel as one cudaMemcpyAsync when the caller vouches for them (F110_HOST_MERGE_ADJACENT): a caller that carves its pinned buffers out of one block per direction
 // (F110HostVecEnv does) pays one PCIe transaction each way per step instead of one per field.
 struct Xfer { char* host; char* dev; size_t bytes; };
 
-int run_xfers(const Xfer* x, int n, cudaMemcpyKind kind, cudaStream_t s) {
+int run_xfers(const Xfer* x, int n, bool merge, cudaMemcpyKind kind, cudaStream_t s) {
     for (int i = 0; i < n;) {
         size_t bytes = x[i].bytes;
         int j = i + 1;
-        while (j < n && x[j].host == x[i].host + bytes && x[j].dev == x[i].dev + bytes) bytes += x[j++].bytes;
+        while (merge && j < n && x[j].host == x[i].host + bytes && x[j].dev == x[i].dev + bytes) bytes += x[j++].bytes;
         if (kind == cudaMemcpyHostToDevice) CUDA_TRY(cudaMemcpyAsync(x[i].dev, x[i].host, bytes, kind, s));
         else CUDA_TRY(cudaMemcpyAsync(x[i].host, x[i].dev, bytes, kind, s));
         i = j;
@@ -455,11 +455,12 @@ int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     SLOT(out, n_out, terminated, N)
     SLOT(out, n_out, collisions, NA)
 #undef SLOT
-    int rc2 = run_xfers(in, n_in, cudaMemcpyHostToDevice, s);
+    const bool merge = (hio->host_flags & F110_HOST_MERGE_ADJACENT) != 0;
+    int rc2 = run_xfers(in, n_in, merge, cudaMemcpyHostToDevice, s);
     if (rc2 != F110_OK) return rc2;
     rc2 = run_step(sim, d, s);
     if (rc2 != F110_OK) return rc2;
-    return run_xfers(out, n_out, cudaMemcpyDeviceToHost, s);
+    return run_xfers(out, n_out, merge, cudaMemcpyDeviceToHost, s);
 }
 
 int f110_host_sync(F110Sim* sim) {

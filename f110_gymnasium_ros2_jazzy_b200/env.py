@@ -301,26 +301,32 @@ class F110HostVecEnv(object):
             self.parts.append(b)
         outs = tuple(dict.fromkeys(tuple(outputs) + ('obs', 'reward', 'terminated')))
         from .backend import _OUT_SPECS
-        # whole-batch outputs.  reward / terminated are plain arrays gathered from the per-chunk blocks after a step;
-        # everything else is pinned and written by the copy engine directly
+        # Every output buffer is a slice of ONE pinned allocation (that is what F110_HOST_MERGE_ADJACENT vouches for).
+        # reward / terminated live in per-chunk [reward f32 | terminated u8] blocks, which the library downloads with one
+        # copy, and are gathered into plain whole-batch arrays after a step; everything else is a whole-batch array
+        # the copy engine writes directly.
+        specs = [(key,) + _OUT_SPECS[key] for key in outs if key not in ('reward', 'terminated')]
+        sizes = [int(np.prod(shape(num_envs, num_agents, num_beams))) * torch.zeros(0, dtype=dt).element_size()
+                 for _, shape, dt in specs]
+        offs = np.cumsum([0] + [(b + 255) // 256 * 256 for b in sizes])
+        small0 = int(offs[-1])
+        self._arena = torch.zeros(small0 + sum((5 * (self.bounds[k + 1] - self.bounds[k]) + 255) // 256 * 256
+                                               for k in range(chunks)), dtype=torch.uint8, pin_memory=True)
         self.out, self._np = {}, {}
-        for key in outs:
-            shape, dtype = _OUT_SPECS[key]
-            if key in ('reward', 'terminated'):
-                self._np[key] = np.zeros(shape(num_envs, num_agents, num_beams), dtype=torch.zeros(0, dtype=dtype).numpy().dtype)
-                self.out[key] = torch.from_numpy(self._np[key])
-            else:
-                self.out[key] = torch.zeros(shape(num_envs, num_agents, num_beams), dtype=dtype, pin_memory=True)
-                self._np[key] = self.out[key].numpy()
-        self._np['terminated'][:] = 1
-        # per chunk: [reward f32 | terminated u8] in one pinned block
-        self._small, self._rew_k, self._term_k = [], [], []
+        for (key, shape, dt), off, nb in zip(specs, offs, sizes):
+            self.out[key] = self._arena[int(off):int(off) + nb].view(dt).view(shape(num_envs, num_agents, num_beams))
+            self._np[key] = self.out[key].numpy()
+        self._np['reward'] = np.zeros(num_envs, np.float32)
+        self._np['terminated'] = np.ones(num_envs, np.uint8)
+        self.out['reward'] = torch.from_numpy(self._np['reward'])
+        self.out['terminated'] = torch.from_numpy(self._np['terminated'])
+        self._rew_k, self._term_k = [], []
+        off = small0
         for k in range(chunks):
             n = self.bounds[k + 1] - self.bounds[k]
-            blk = torch.zeros(5 * n, dtype=torch.uint8, pin_memory=True)
-            self._small.append(blk)
-            self._rew_k.append(blk[:4 * n].view(torch.float32).numpy())
-            self._term_k.append(blk[4 * n:].numpy())
+            self._rew_k.append(self._arena[off:off + 4 * n].view(torch.float32).numpy())
+            self._term_k.append(self._arena[off + 4 * n:off + 5 * n].numpy())
+            off += (5 * n + 255) // 256 * 256
         self._in = {}            # action dtype -> per-chunk input blocks (built at the first step with that dtype)
         self.start_poses = None
 
@@ -345,6 +351,7 @@ class F110HostVecEnv(object):
             m = blk[ab + n * A * 24:].numpy()
             io = ios[k]
             io.actions, io.actions_f64 = a.ctypes.data, int(dtype == np.float64)
+            io.host_flags = _lib.F110_HOST_MERGE_ADJACENT      # adjacent buffers below are slices of one pinned block
             io.reset_poses, io.reset_mask = p.ctypes.data, m.ctypes.data
             io.reward, io.terminated = self._rew_k[k].ctypes.data, self._term_k[k].ctypes.data
             for key, t in self.out.items():

@@ -95,12 +95,16 @@ typedef struct F110Config {
     uint64_t seed;         /* seed of the on-device Philox noise stream */
 } F110Config;
 
+/* F110StepIO.host_flags: the caller states that host buffers lying exactly back to back were carved out of ONE pinned
+ * allocation, so that one copy may span them (see f110_step_host_async).  Without it every field is copied by itself. */
+#define F110_HOST_MERGE_ADJACENT 1
+
 /* One step over the whole batch.  Inputs may be NULL where noted; NULL outputs are skipped. */
 typedef struct F110StepIO {
     /* ---- inputs */
     const void* actions;         /* [N][A][2] (steer, speed); f32 or f64, see actions_f64.  NULL = zero action */
     int32_t actions_f64;         /* 0: float (train_ddpg.py:171), 1: double (gym_bridge.py:226-228) */
-    int32_t reserved0;
+    int32_t host_flags;          /* host path only (f110_step_host*): F110_HOST_MERGE_ADJACENT or 0 */
     const double* noise;         /* [N][A][B] additive lidar noise drawn by the caller (parity mode: numpy's
                                     Generator.normal stream, laser_models.py:450-452); NULL = on-device
                                     Philox2x32-10 + Box-Muller N(0, noise_std^2) */
@@ -159,10 +163,10 @@ int f110_step(F110Sim* sim, const F110StepIO* io, void* stream);
 int f110_step_host(F110Sim* sim, const F110StepIO* io);
 /* The same without the final synchronisation: the host buffers are valid after f110_host_sync().  Lets a caller
  * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels.
- * Fields whose host buffers lie exactly back to back in the order
+ * With F110_HOST_MERGE_ADJACENT in io->host_flags, fields whose host buffers lie exactly back to back in the order
  *     inputs : actions, reset_poses, noise, reset_mask, active_mask
  *     outputs: obs, scans_f32, reward, toggles, scans_f64, state, lap_times, lap_counts, time, terminated, collisions
- * (absent fields skipped) are moved by a single copy per direction; any other placement works, one copy per field. */
+ * (absent fields skipped) are moved by a single copy per direction; fields placed otherwise get one copy each. */
 int f110_step_host_async(F110Sim* sim, const F110StepIO* io);
 int f110_host_sync(F110Sim* sim);
 /* f110_step_host_async on `count` handles (ios[i] belongs to sims[i]), then f110_host_sync on each: one call per step

@@ -10,6 +10,7 @@ What is recorded
                    the Shanghai centerline start poses, and the numpy-computed
                    lookup tables (laser_models.py:379-381, base_classes.py:122-158).
   scans.npz        noise-free ScanSimulator2D.scan(pose, None) at fixed poses.
+  scans_rotated.npz  the same on a map whose yaml origin has a yaw (the rotated branch of xy_2_rc).
   rollout_*.npz    F110Env / Simulator rollouts: per-step fp64 states, flags, lap bookkeeping,
                    and sub-sampled scans / flat observations.
 """
@@ -255,12 +256,40 @@ def make_reward_golden():
     print('reward.npz', len(rew_all), 'steps; reward range', min(rew_all), max(rew_all), 'alt', min(rew2_all), max(rew2_all))
 
 
+def make_rotated_scan_golden(theta=0.3):
+    """ScanSimulator2D on the Shanghai image under a yaml whose origin has a yaw (laser_models.py:410-422 keeps
+    orig_c / orig_s; xy_2_rc rotates every lookup, :70-77) -> tests/golden/scans_rotated.npz"""
+    import shutil
+    from f110_gym.envs.laser_models import ScanSimulator2D
+    shutil.copy(os.path.join(REF_MAPS, 'Shanghai_map.png'), os.path.join(TMP, 'Shanghai_rot.png'))
+    origin = [3.5, -7.25, theta]
+    with open(os.path.join(TMP, 'Shanghai_rot.yaml'), 'w') as f:
+        f.write("image: Shanghai_rot.png\nresolution: 0.06505\norigin: [%r, %r, %r]\nnegate: 0\noccupied_thresh: 0.45\n"
+                "free_thresh: 0.196\n" % tuple(origin))
+    sim = ScanSimulator2D(1080, 4.7)
+    sim.set_map(os.path.join(TMP, 'Shanghai_rot.yaml'), '.png')
+    m = dict(np.load(os.path.join(HERE, 'maps.npz')))
+    cl, o = m['Shanghai_map__centerline_poses'], m['Shanghai_map__origin']
+    cl = cl[np.linspace(0, len(cl) - 1, 48).round().astype(int)]
+    mx, my = cl[:, 0] - o[0], cl[:, 1] - o[1]                      # map-frame coordinates of the centerline
+    c, s_ = np.cos(theta), np.sin(theta)
+    poses = np.stack([origin[0] + c * mx - s_ * my, origin[1] + s_ * mx + c * my, cl[:, 2] + theta], axis=1)
+    poses = np.concatenate([poses, [[0., 0., 0.], [500., 0., 1.]]])     # in free space or not, and outside the map
+    scans = np.stack([sim.scan(p, None) for p in poses])
+    np.savez_compressed(os.path.join(HERE, 'scans_rotated.npz'), origin=np.array(origin), poses=poses, scans=scans,
+                        orig_c=np.float64(sim.orig_c), orig_s=np.float64(sim.orig_s))
+    print('scans_rotated.npz', scans.shape, 'range', scans.min(), scans.max())
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'reward':
         make_reward_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == 'gap_follow':
         make_gap_follow_golden()     # only the consumer-side fixture
+    elif len(sys.argv) > 1 and sys.argv[1] == 'rotated':
+        make_rotated_scan_golden()
     else:
         main()
         make_gap_follow_golden()
         make_reward_golden()
+        make_rotated_scan_golden()

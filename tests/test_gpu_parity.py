@@ -137,6 +137,28 @@ def test_exact_finishing_path_scans(theta):
         assert d.max() == 0.0
 
 
+def test_rotated_origin_scans_golden():
+    """Map origin with a yaw (non-identity rotation in every lookup): against the reference's own scans."""
+    _torch()
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+    g = H.load('scans_rotated')
+    dt, res, _ = H.golden_map('Shanghai_map')
+    poses = g['poses']
+    n = len(poses)
+    sim = BatchSim(n, 1, outputs=ALL_OUTPUTS, noise_std=0.0)
+    s, c, _, _, _ = H.tables()
+    sim.set_tables(s, c)
+    sim.set_map_arrays(dt, res, [float(v) for v in g['origin']])
+    sim.sim_reset(poses[:, None, :])
+    o = sim.step(None, np.zeros((n, 1, 1080)))
+    torch.cuda.synchronize()
+    d = np.abs(o['scans_f64'].cpu().numpy()[:, 0] - g['scans'])
+    print('rotated origin: max', d.max(), 'exact fraction', float((d == 0).mean()))
+    assert (d <= SCAN_TOL).mean() >= SCAN_FRAC
+    sim.close()
+
+
 def test_c1_single_agent_sim_rollout():
     g = H.load('rollout_c1_single')
     be = make_gpu(1, 'Shanghai_map')

@@ -112,6 +112,22 @@ def test_scans_bit_exact(map_name):
         assert np.array_equal(mine, ref)
 
 
+def test_scans_rotated_origin():
+    """yaml origin with a yaw: the rotated branch of xy_2_rc (laser_models.py:70-77), golden from the reference."""
+    from oracle.f110_oracle import Oracle
+    g = H.load('scans_rotated')
+    dt, res, _ = H.golden_map('Shanghai_map')
+    o = Oracle(1, 1)
+    o.set_map_arrays(dt, res, [float(v) for v in g['origin']])
+    s, c, _, _, _ = H.tables()
+    o.set_tables(s, c)
+    d = np.abs(np.stack([o.scan(p)[0] for p in g['poses']]) - g['scans'])
+    # the oracle takes cos/sin(origin yaw) from libm, the reference from numpy: equal here, else allow the 1e-6 bar
+    print('rotated origin: max', d.max(), 'exact fraction', float((d == 0).mean()))
+    assert (d <= 1e-6).mean() >= 0.999
+    assert d.max() == 0.0 or not (np.cos(g['origin'][2]) == g['orig_c'] and np.sin(g['origin'][2]) == g['orig_s'])
+
+
 def test_dt_probe():
     dt, res, _ = H.golden_map('Shanghai_map')
     p = H.load('scans')['Shanghai_map__dt_probe']
