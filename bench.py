@@ -331,7 +331,10 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
                     "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar, "longest_ray_lookups": max_lookups,
-                    "bytes_per_ray": bytes_per_ray, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                    "bytes_per_ray": bytes_per_ray,
+                    "sector_level": {"bytes_per_ray": 32.0 * lbar + 8.0, "gbs": (32.0 * lbar + 8.0) * E * A * B / (lidar_ms * 1e-3) / 1e9,
+                                     "note": "32-byte sector per gather instead of the 8 useful bytes (SURVEY 8d)"},
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                     "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]},
                     "gather_roofline": dict(gather, frac_of_whole_map=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["whole_map_gbs"],
                                             frac_of_touched_window=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["touched_window_gbs"])}
@@ -444,6 +447,14 @@ def gather_roofline(dt, rays, lbar, torch, dev):
         _lib.check(L.f110_gather_probe(C.c_void_p(m.data_ptr()), m.numel(), window, chain, int(rays), 5,
                                        C.c_void_p(sink.data_ptr()), C.byref(ms), None))
         out[key] = 8.0 * chain * rays / (ms.value * 1e-3) / 1e9
+    # the HBM-resident regime (an array far larger than L2), for the C4 large-map sweep
+    del m
+    big = torch.zeros(2 * 1024 ** 3 // 8, dtype=torch.float64, device=dev)
+    ms = C.c_float(0)
+    _lib.check(L.f110_gather_probe(C.c_void_p(big.data_ptr()), big.numel(), 0, chain, int(rays), 3,
+                                   C.c_void_p(sink.data_ptr()), C.byref(ms), None))
+    out["hbm_2gib_gbs"] = 8.0 * chain * rays / (ms.value * 1e-3) / 1e9
+    del big
     return out
 
 
