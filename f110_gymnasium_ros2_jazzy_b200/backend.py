@@ -38,6 +38,10 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class HostBlocks(object):
+    """The pinned buffers of BatchSim.host_blocks (plain attribute bag)."""
+
+
 class BatchSim(object):
     """Device-resident batch of F110 simulations (the native backend of Simulator + F110Env.step)."""
 
@@ -229,6 +233,54 @@ class BatchSim(object):
         else:
             _lib.check(self.lib.f110_step_host_async(self.h, C.byref(io)))
         return out
+
+    # merge order of f110_step_host_async (include/f110_b200.h)
+    _IN_ORDER = ('actions', 'reset_poses', 'noise', 'reset_mask')
+    _OUT_ORDER = ('scans_f64', 'state', 'lap_times', 'lap_counts', 'time', 'obs', 'scans_f32', 'reward', 'toggles',
+                  'terminated', 'collisions')
+
+    def host_blocks(self, outputs=ALL_OUTPUTS, actions_dtype=np.float32, noise=True):
+        """Pinned host buffers for step_host_blocks: one allocation per direction, the fields back to back in the
+        library's merge order, so that a step moves them with ONE copy each way (F110_HOST_MERGE_ADJACENT).
+        -> HostBlocks with numpy views .actions [N,A,2], .reset_poses [N,A,3], .noise [N,A,B] (or None),
+        .reset_mask [N] and the dict .out of output views."""
+        N, A, B = self.N, self.A, self.B
+        adt = np.dtype(actions_dtype)
+        hb = HostBlocks()
+        in_specs = {'actions': ((N, A, 2), adt), 'reset_poses': ((N, A, 3), np.dtype(np.float64)),
+                    'noise': ((N, A, B), np.dtype(np.float64)), 'reset_mask': ((N,), np.dtype(np.uint8))}
+        keys = [k for k in self._IN_ORDER if noise or k != 'noise']
+        nbytes = [int(np.prod(in_specs[k][0])) * in_specs[k][1].itemsize for k in keys]
+        hb._in = torch.zeros(sum(nbytes), dtype=torch.uint8, pin_memory=True)
+        raw, off = hb._in.numpy(), 0
+        hb.noise = None
+        for k, nb in zip(keys, nbytes):
+            setattr(hb, k, raw[off:off + nb].view(in_specs[k][1]).reshape(in_specs[k][0]))
+            off += nb
+        okeys = [k for k in self._OUT_ORDER if k in outputs]
+        onb = [int(np.prod(_OUT_SPECS[k][0](N, A, B))) * torch.zeros(0, dtype=_OUT_SPECS[k][1]).element_size() for k in okeys]
+        hb._out = torch.zeros(sum(onb), dtype=torch.uint8, pin_memory=True)
+        hb.out, off = {}, 0
+        for k, nb in zip(okeys, onb):
+            hb.out[k] = hb._out[off:off + nb].view(_OUT_SPECS[k][1]).view(_OUT_SPECS[k][0](N, A, B))
+            off += nb
+        hb.np = {k: v.numpy() for k, v in hb.out.items()}
+        hb.io = _lib.F110StepIO(actions=C.c_void_p(hb.actions.ctypes.data), actions_f64=int(adt == np.float64),
+                                host_flags=_lib.F110_HOST_MERGE_ADJACENT,
+                                noise=None if hb.noise is None else C.c_void_p(hb.noise.ctypes.data),
+                                reset_mask=C.c_void_p(hb.reset_mask.ctypes.data),
+                                reset_poses=C.c_void_p(hb.reset_poses.ctypes.data), active_mask=None,
+                                **{k: C.c_void_p(v.data_ptr()) for k, v in hb.out.items()})
+        return hb
+
+    def step_host_blocks(self, hb, sync=True):
+        """One step on the buffers of host_blocks(): the caller has filled hb.actions / hb.noise / hb.reset_mask
+        (non-zero: that env is reset to hb.reset_poses and its action ignored)."""
+        if sync:
+            _lib.check(self.lib.f110_step_host(self.h, C.byref(hb.io)))
+        else:
+            _lib.check(self.lib.f110_step_host_async(self.h, C.byref(hb.io)))
+        return hb.np
 
     def host_sync(self):
         _lib.check(self.lib.f110_host_sync(self.h))

@@ -439,19 +439,17 @@ int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     SLOT(in, n_in, reset_mask, N)
     SLOT(in, n_in, active_mask, N)
     cur = sim->io_blob + (((size_t)(cur - sim->io_blob) + 255) & ~size_t(255));
-    // outputs, in merge order: obs, scans_f32, reward (f32), toggles (i32) | scans_f64, state, lap_times, lap_counts,
-    // time (f64) | terminated, collisions (bytes).  The 4-byte group holds an even number of words whenever the f64
-    // group follows a complete one (N * (B + 8) + N is even for even N); otherwise one pad word keeps f64 aligned.
-    SLOT(out, n_out, obs, N * (B + 8) * sizeof(float))
-    SLOT(out, n_out, scans_f32, NA * B * sizeof(float))
-    SLOT(out, n_out, reward, N * sizeof(float))
-    SLOT(out, n_out, toggles, NA * sizeof(int32_t))
-    cur = sim->io_blob + (((size_t)(cur - sim->io_blob) + 7) & ~size_t(7));
+    // outputs, in merge order: the 8-byte fields, then the 4-byte ones, then the byte arrays -- no padding is ever needed
+    // between two of them.  (With only obs / reward / terminated requested, obs sits at the 256-byte aligned start.)
     SLOT(out, n_out, scans_f64, NA * B * sizeof(double))
     SLOT(out, n_out, state, NA * 7 * sizeof(double))
     SLOT(out, n_out, lap_times, NA * sizeof(double))
     SLOT(out, n_out, lap_counts, NA * sizeof(double))
     SLOT(out, n_out, time, N * sizeof(double))
+    SLOT(out, n_out, obs, N * (B + 8) * sizeof(float))
+    SLOT(out, n_out, scans_f32, NA * B * sizeof(float))
+    SLOT(out, n_out, reward, N * sizeof(float))
+    SLOT(out, n_out, toggles, NA * sizeof(int32_t))
     SLOT(out, n_out, terminated, N)
     SLOT(out, n_out, collisions, NA)
 #undef SLOT

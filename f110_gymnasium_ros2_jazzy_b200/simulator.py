@@ -48,7 +48,7 @@ class Simulator(object):
         self._rngs = None
         self._pending_reset = None
         self.last = None
-        self._host_out = None
+        self._blocks = {}        # action dtype -> pinned host blocks
 
     def set_map(self, map_path, map_ext):
         self.backend.set_map(map_path, map_ext, edt=self.edt)
@@ -66,21 +66,33 @@ class Simulator(object):
         torch.cuda.current_stream(self.backend.device).synchronize()   # the host-buffer step runs on the library's own stream
         self._rngs = [np.random.default_rng(seed=self.seed) for _ in range(self.num_agents)]
 
-    def _noise(self):
-        if self.noise_mode != 'numpy':
-            return None
+    def _fill_noise(self, dst):
+        """dst [1, A, B]: one normal(0, 0.01) draw per car from its own generator (laser_models.py:450-452)."""
         if self._rngs is None:
             raise AttributeError("scan_rng is only created by reset() for cars other than the first (base_classes.py:119,204)")
-        return np.stack([r.normal(0., 0.01, size=self.num_beams) for r in self._rngs])[None]
+        for i, r in enumerate(self._rngs):
+            dst[0, i] = r.normal(0., 0.01, size=self.num_beams)
 
     def _step_raw(self, control_inputs, reset_mask=None, reset_poses=None):
-        """One f110_step_host call: actions / noise up, kernels, every output down into pinned buffers, one sync.
-        The returned arrays are views of those buffers (rewritten by the next step); callers copy what they keep."""
-        if self._host_out is None:
-            self._host_out = self.backend.host_out(ALL_OUTPUTS)
-            self._host_np = {k: v.numpy() for k, v in self._host_out.items()}
-        self.backend.step_host(control_inputs, self._noise(), reset_mask, reset_poses, out=self._host_out)
-        self.last = self._host_np
+        """One f110_step_host call: actions / noise up, kernels, every output down, one sync.  Inputs and outputs live
+        in one pinned block per direction (BatchSim.host_blocks), so each direction is a single PCIe copy.
+        The returned arrays are views of the output block (rewritten by the next step); callers copy what they keep."""
+        dt = np.dtype(np.float32) if control_inputs is None else control_inputs.dtype
+        hb = self._blocks.get(dt)
+        if hb is None:
+            hb = self._blocks[dt] = self.backend.host_blocks(ALL_OUTPUTS, actions_dtype=dt, noise=self.noise_mode == 'numpy')
+        if control_inputs is None:
+            hb.actions[...] = 0
+        else:
+            hb.actions[...] = control_inputs
+        if hb.noise is not None:
+            self._fill_noise(hb.noise)
+        if reset_mask is None:
+            hb.reset_mask[...] = 0
+        else:
+            hb.reset_mask[...] = reset_mask
+            hb.reset_poses[...] = reset_poses
+        self.last = self.backend.step_host_blocks(hb)
         return self.last
 
     def step(self, control_inputs):

@@ -165,7 +165,7 @@ int f110_step_host(F110Sim* sim, const F110StepIO* io);
  * that shards its envs over several handles overlap one shard's PCIe copies with another shard's kernels.
  * With F110_HOST_MERGE_ADJACENT in io->host_flags, fields whose host buffers lie exactly back to back in the order
  *     inputs : actions, reset_poses, noise, reset_mask, active_mask
- *     outputs: obs, scans_f32, reward, toggles, scans_f64, state, lap_times, lap_counts, time, terminated, collisions
+ *     outputs: scans_f64, state, lap_times, lap_counts, time, obs, scans_f32, reward, toggles, terminated, collisions
  * (absent fields skipped) are moved by a single copy per direction; fields placed otherwise get one copy each. */
 int f110_step_host_async(F110Sim* sim, const F110StepIO* io);
 int f110_host_sync(F110Sim* sim);
