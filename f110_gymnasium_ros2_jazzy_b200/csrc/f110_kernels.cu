@@ -385,8 +385,9 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
     // lookups, p99 42, max ~300 on the Shanghai map), so a long ray that starts in the last wave of CTAs leaves
     // most SMs idle while it finishes.  A ray's length changes little from one step to the next, so every warp
     // records whether its unit was long (>= HEAVY_ITERS lookups) and the next step's grid runs those units FIRST,
-    // in a front region of sc.front_units warps (order_publish_kernel hands the history over); the remaining warps walk the units in natural order and skip the
-    // ones the front region took.  Only the launch order depends on this history, never a result.
+    // in a front region of sc.front_units warps (the post kernel latches the count, the dynamics kernel publishes the
+    // list); the remaining warps walk the units in natural order and skip the ones the front region took.  Only the
+    // launch order depends on this history, never a result.
     const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
     unsigned unit;
