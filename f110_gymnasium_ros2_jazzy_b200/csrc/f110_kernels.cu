@@ -144,37 +144,73 @@ __device__ __forceinline__ void pid(double speed, double steer, double cur_speed
 __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     cudaGridDependencySynchronize();   // PDL: the previous step's post kernel (or whatever precedes in the stream) is done
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    {
-        // Publish the launch-order history the lidar kernel recorded during the previous step (the "next" halves
-        // of the buffers; its length was latched into heavy_cnt[0] by the post kernel) as this step's order.  A copy
-        // rather than a pointer flip, so a captured CUDA graph stays valid step after step.
-        const unsigned stride = gridDim.x * blockDim.x;
-        const unsigned nw = sc.num_units / 4;                        // num_units is padded to a multiple of 4
-        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units);
-        uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sc.unit_heavy);
-        for (unsigned base = s; base < nw; base += 8 * stride) {     // 8 independent loads in flight per thread
-            uint32_t v[8];
+    // Every global load this thread needs is issued before the first store or branch that depends on one: the kernel is a
+    // single dependent chain per thread, and with a cold L2 each load left in program order behind a branch costs a DRAM
+    // round trip of its own (the publish copy, the masks, the state, the action and the parameters were five in a row).
+    //
+    // (1) The launch-order history the lidar kernel recorded during the previous step (the "next" halves of the
+    // buffers; its length was latched into heavy_cnt[0] by the post kernel) becomes this step's order.  A copy rather
+    // than a pointer flip, so a captured CUDA graph stays valid step after step.
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned nw = sc.num_units / 4;                        // num_units is padded to a multiple of 4
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units);
+    uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sc.unit_heavy);
+    uint32_t v0[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; v[j] = k < nw ? src[k] : 0u; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; if (k < nw) dst[k] = v[j]; }
-        }
-        const unsigned n = sc.heavy_cnt[0];
-        for (unsigned k = s; k < n; k += stride) sc.heavy_list[k] = sc.heavy_list[sc.front_units + k];
-    }
-    if (s >= c.NA) return;
-    const int env = s / c.A;
+    for (int j = 0; j < 8; ++j) { const unsigned k = (unsigned)s + j * stride; v0[j] = k < nw ? src[k] : 0u; }
+    const unsigned n_heavy = sc.heavy_cnt[0];
+    const unsigned heavy0 = (unsigned)s < sc.front_units ? sc.heavy_list[sc.front_units + s] : 0u;   // used only if s < n_heavy
+
+    // (2) this thread's vehicle
+    const bool veh = s < c.NA;
+    const int env = veh ? s / c.A : 0;
     const int a = s - env * c.A;
-    if (io.active_mask && !io.active_mask[env]) return;
-    const bool rst = io.reset_mask && io.reset_mask[env];
+    uint8_t active = 1, rst_flag = 0;
+    double xl[7] = {0., 0., 0., 0., 0., 0., 0.}, b0 = 0., b1 = 0., px = 0., py = 0., pth = 0.;
+    int cnt = 0;
+    double raw_steer = 0., speed = 0.;
+    if (veh) {
+        if (io.active_mask) active = io.active_mask[env];
+        if (io.reset_mask) {
+            rst_flag = io.reset_mask[env];
+            const double* ps = io.reset_poses + (size_t)s * 3;
+            px = ps[0]; py = ps[1]; pth = ps[2];
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) xl[k] = st.x[k][s];
+        b0 = st.steer_buf0[s]; b1 = st.steer_buf1[s];
+        cnt = st.steer_cnt[s];
+        if (io.actions) {
+            if (io.actions_f64) {
+                const double2 v = reinterpret_cast<const double2*>(io.actions)[s];
+                raw_steer = v.x; speed = v.y;
+            } else {
+                const float2 v = reinterpret_cast<const float2*>(io.actions)[s];
+                raw_steer = (double)v.x; speed = (double)v.y;
+            }
+        }
+    }
+    const VehParams p = load_params(c.params + (veh ? a : 0) * F110_NUM_PARAMS);
+
+    // (1, continued) the stores of the copy
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const unsigned k = (unsigned)s + j * stride; if (k < nw) dst[k] = v0[j]; }
+    for (unsigned base = (unsigned)s + 8 * stride; base < nw; base += 8 * stride) {   // batches the grid does not cover at once
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; v[j] = k < nw ? src[k] : 0u; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; if (k < nw) dst[k] = v[j]; }
+    }
+    if ((unsigned)s < n_heavy) sc.heavy_list[s] = heavy0;
+    for (unsigned k = (unsigned)s + stride; k < n_heavy; k += stride) sc.heavy_list[k] = sc.heavy_list[sc.front_units + k];
+
+    if (!veh || !active) return;
+    const bool rst = rst_flag != 0;
 
     double x[7];
-    double b0, b1;
-    int cnt;
     if (rst) {
         // F110Env.reset bookkeeping (f110_env.py:440-451) + RaceCar.reset (base_classes.py:183-204)
-        const double* ps = io.reset_poses + (size_t)s * 3;
-        const double px = ps[0], py = ps[1], pth = ps[2];
         x[0] = px; x[1] = py; x[2] = 0.; x[3] = 0.; x[4] = pth; x[5] = 0.; x[6] = 0.;
         b0 = b1 = 0.;
         cnt = 0;
@@ -188,23 +224,11 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
             st.rot_s[env] = sin(th);
         }
         if (a == 0) { st.time[env] = 0.0; st.step_count[env] = 0u; }
+        raw_steer = 0.; speed = 0.;   // the reset's own step uses a zero action (f110_env.py:457-458)
     } else {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) x[k] = st.x[k][s];
-        b0 = st.steer_buf0[s]; b1 = st.steer_buf1[s];
-        cnt = st.steer_cnt[s];
+        for (int k = 0; k < 7; ++k) x[k] = xl[k];
         if (a == 0) st.step_count[env] += 1u;
-    }
-
-    double raw_steer = 0., speed = 0.;
-    if (!rst && io.actions) {   // the reset's own step uses a zero action (f110_env.py:457-458)
-        if (io.actions_f64) {
-            const double2 v = reinterpret_cast<const double2*>(io.actions)[s];
-            raw_steer = v.x; speed = v.y;
-        } else {
-            const float2 v = reinterpret_cast<const float2*>(io.actions)[s];
-            raw_steer = (double)v.x; speed = (double)v.y;
-        }
     }
 
     // steering delay FIFO, base_classes.py:270-278
@@ -213,7 +237,6 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
     else steer = b1;
     b1 = b0; b0 = raw_steer;
 
-    const VehParams p = load_params(c.params + a * F110_NUM_PARAMS);
     double accl, sv;
     pid(speed, steer, x[3], x[2], p, accl, sv);
     sv = clipd(sv, p.sv_min, p.sv_max);         // :283
