@@ -244,20 +244,26 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
 
     const double dt = c.timestep;
     if (c.integrator == F110_INTEGRATOR_RK4) {  // :285-374
-        double k1[7], k2[7], k3[7], k4[7], xs[7];
-        vehicle_dynamics_st(x, sv, accl, p, k1);
+        // One copy of the right-hand side, run four times, instead of four inlined copies: the kernel's instruction
+        // stream is fetched cold by every SM, and the stages cannot overlap anyway.  Bit-identical to the reference's
+        // unrolled form: k/2 == k*0.5 and 2*k are exact, k*1.0 == k, and k1 + 2*k2 + 2*k3 + k4 is summed left to right.
+        double sum[7], xs[7], k[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * (k1[i] / 2);
-        vehicle_dynamics_st(xs, sv, accl, p, k2);
+        for (int i = 0; i < 7; ++i) { xs[i] = x[i]; sum[i] = 0.; }
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            vehicle_dynamics_st(xs, sv, accl, p, k);
+            const double wgt = (stage == 1 || stage == 2) ? 2.0 : 1.0;    // weight in the final sum
+            const double half = stage < 2 ? 0.5 : 1.0;                    // k/2 for the two midpoint stages, k for the last
 #pragma unroll
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * (k2[i] / 2);
-        vehicle_dynamics_st(xs, sv, accl, p, k3);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + dt * k3[i];
-        vehicle_dynamics_st(xs, sv, accl, p, k4);
+            for (int i = 0; i < 7; ++i) {
+                sum[i] = stage == 0 ? k[i] : sum[i] + wgt * k[i];
+                xs[i] = x[i] + dt * (k[i] * half);
+            }
+        }
         const double w = dt * (1.0 / 6.0);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) x[i] = x[i] + w * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+        for (int i = 0; i < 7; ++i) x[i] = x[i] + w * sum[i];
     } else {                                    // Euler :376-396
         double f[7];
         vehicle_dynamics_st(x, sv, accl, p, f);
