@@ -198,7 +198,7 @@ def reference_main(args):
         "e2e": {"value": r['value'], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -212,7 +212,22 @@ def workload_config(args, envs_per_gpu, note=None):
     return c
 
 
+def emit(line):
+    """The one JSON line, on the process's ORIGINAL stdout (see main)."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
+_JSON_OUT = sys.stdout
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL prints its version banner there when NCCL_DEBUG is set in the
+    # environment).  Keep the original stdout for the JSON line and point fd 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         return reference_main(args)
@@ -363,7 +378,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
