@@ -406,6 +406,8 @@ def e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch):
     downloads observation / reward / terminated into pinned host memory, inside the timed region (wall clock
     around K synchronous steps).  Returns elapsed seconds."""
     from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv
+    from f110_gymnasium_ros2_jazzy_b200.dist import bind_host_to_gpu
+    previous_affinity = bind_host_to_gpu(local) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None   # NUMA-local pinned buffers
     hc = [int(v) for v in str(args.host_chunks).split(",")]
     henv = F110HostVecEnv(E, chunks=hc[0] if len(hc) == 1 else tuple(hc), map_arrays=map_arrays, num_agents=A, num_beams=B,
                           device=local, noise_std=0.01)
@@ -443,6 +445,8 @@ def e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch):
         henv.recv(g)
     el_pipe = time.perf_counter() - t0
     henv.close()
+    if previous_affinity is not None:
+        os.sched_setaffinity(0, previous_affinity)
     return el, el_pipe
 
 

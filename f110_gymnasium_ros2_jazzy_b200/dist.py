@@ -12,6 +12,41 @@ def shard_range(num_envs, rank, world_size):
     return lo, hi
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index, pci_bus_id=None, sysfs='/sys'):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates afterwards (first touch) and the threads that fill them sit next to that GPU's PCIe root.  With one
+    process per GPU on a two-socket box this keeps the per-step observation downloads off the socket interconnect.
+    Returns the previous affinity (hand it to os.sched_setaffinity to undo) or None when nothing was changed
+    (single node, no sysfs entry, affinity already narrower)."""
+    import os
+    try:
+        if pci_bus_id is None:
+            p = torch.cuda.get_device_properties(device_index)
+            pci_bus_id = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(os.path.join(sysfs, 'bus/pci/devices', pci_bus_id.lower(), 'numa_node')).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)).read())
+        before = os.sched_getaffinity(0)
+        want = cpus & before
+        if not want or want == before:
+            return None
+        os.sched_setaffinity(0, want)
+        return before
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 class EpisodeStats(object):
     """Sum-reduces the per-rank episode counters (BatchSim.stats) across ranks.
 

@@ -152,3 +152,29 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.decode().strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'env-steps/s' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_bind_host_to_gpu_uses_the_gpus_numa_node(tmp_path):
+    """bind_host_to_gpu reads <sysfs>/bus/pci/devices/<id>/numa_node and node<N>/cpulist; here against a fake sysfs."""
+    import os
+    from f110_gymnasium_ros2_jazzy_b200.dist import _parse_cpulist, bind_host_to_gpu
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    before = os.sched_getaffinity(0)
+    if len(before) < 2:
+        pytest.skip("needs two CPUs")
+    keep = sorted(before)[: len(before) // 2]
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text(",".join(str(c) for c in keep) + "\n")
+    try:
+        prev = bind_host_to_gpu(0, pci_bus_id="0000:1B:00.0", sysfs=str(tmp_path))
+        assert prev == before and os.sched_getaffinity(0) == set(keep)
+        # no NUMA information (-1) or an unknown device: nothing changes
+        (dev / "numa_node").write_text("-1\n")
+        assert bind_host_to_gpu(0, pci_bus_id="0000:1b:00.0", sysfs=str(tmp_path)) is None
+        assert bind_host_to_gpu(0, pci_bus_id="0000:ff:00.0", sysfs=str(tmp_path)) is None
+    finally:
+        os.sched_setaffinity(0, before)
