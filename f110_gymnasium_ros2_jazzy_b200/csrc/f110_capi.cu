@@ -61,6 +61,7 @@ struct F110Sim {
     bool map_set = false;
     bool count_lookups = false;
     bool narrow_fraction = false;
+    bool debug_sync = false;
     // device memory
     char* state_blob = nullptr;   size_t state_bytes = 0;    // checkpointable
     char* scratch_blob = nullptr; size_t scratch_bytes = 0;
@@ -138,11 +139,21 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
         for (int i = 0; i < 4; ++i) { CUDA_TRY(cudaEventCreate(&e[i])); sim->tev.push_back(e[i]); }
         CUDA_TRY(cudaEventRecord(e[0], s));
     }
+    // F110_DEBUG_SYNC=1 in the environment: wait for each kernel and name the one that faulted
+#define DEBUG_SYNC(name)                                                                                           \
+    if (sim->debug_sync) {                                                                                         \
+        const cudaError_t de = cudaStreamSynchronize(s);                                                           \
+        if (de != cudaSuccess) return fail(F110_ERR_CUDA, "%s: %s", name, cudaGetErrorString(de));                 \
+    }
     launch_dynamics(sim->c, sim->st, sim->sc, io, s);
+    DEBUG_SYNC("dynamics_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[1], s));
     launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_threads, s);
+    DEBUG_SYNC("lidar_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
     launch_post(sim->c, sim->st, sim->sc, io, s);
+    DEBUG_SYNC("post_kernel")
+#undef DEBUG_SYNC
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
     sim->launches += 3;
     CUDA_TRY(cudaPeekAtLastError());
@@ -181,6 +192,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     const int N = cfg->num_envs, A = cfg->num_agents, B = cfg->num_beams, NA = N * A;
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
     sim->narrow_fraction = (cfg->flags & F110_FLAG_NARROW_FRACTION) != 0;
+    sim->debug_sync = getenv("F110_DEBUG_SYNC") != nullptr;
     if (const char* e = getenv("F110_LIDAR_THREADS")) {   // tuning knob, multiple of 32 in [32, 256]
         const int t = atoi(e);
         if (t >= 32 && t <= 128 && t % 32 == 0) sim->lidar_threads = t;

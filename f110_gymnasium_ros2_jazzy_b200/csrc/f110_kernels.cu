@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_ker
             }
         }
         int ti = (int)t;
-        ti = ti < c.theta_dis ? ti : c.theta_dis - 1;   // memory safety only
+        // memory safety only: a NaN yaw (a car poisoned by a NaN command) converts to a NEGATIVE index on this hardware
+        ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
         const double sn = __ldg(c.sines + ti);
         const double cs = __ldg(c.cosines + ti);
 

@@ -224,6 +224,37 @@ def test_batched_vs_oracle(num_envs, num_agents):
     assert stats['outl'] <= (1 - SCAN_FRAC) * stats['beams']
 
 
+def test_non_finite_actions():
+    """NaN / inf commands.  A NaN steer is swallowed by pid (its comparison is false) and an infinite speed by the
+    acceleration clip: both match the oracle (and the reference, probed in the build container) to the usual
+    tolerances.  A NaN speed or an infinite steer (pid forms inf/inf) poisons the state; the reference -- and the
+    oracle, which restates it -- then index the map with int(NaN) and segfault, so there is nothing to be equal to:
+    here those envs must stay memory-safe and must not disturb their neighbours."""
+    poses = np.array([[0., 0., 0.], [3.0, 0.5, 0.]])
+    bad = [[np.nan, 3.0], [0.1, np.inf], [0.05, 3.0], [np.nan, np.nan], [-np.inf, 2.0]]
+    N, M = len(bad), 3                                      # the first M envs have a counterpart in the oracle
+    be = GpuBackend(N, 2, 'Shanghai_map')
+    orc = make_oracle(M, 2, 'Shanghai_map')
+    rng = np.random.default_rng(9)
+    P = np.broadcast_to(poses, (N, 2, 3)).copy()
+    for t in range(45):
+        noise = rng.normal(0, 0.01, size=(N, 2, 1080))
+        if t == 0:
+            g = be.reset(P, noise); c = orc.reset(P[:M], noise[:M])
+        else:
+            act = np.tile(np.array([[0.05, 3.0], [0.0, 2.0]]), (N, 1, 1))
+            if t == 20:
+                act[:, 0] = bad
+            g = be.step(act, noise); c = orc.step(act[:M], noise[:M])
+        for k in ('collisions', 'terminated', 'toggles'):
+            assert np.array_equal(g[k][:M], c[k]), (k, t)
+        assert np.abs(g['state'][:M] - c['state']).max() <= STATE_TOL, t
+        assert (np.abs(g['scans'][:M] - c['scans']) <= SCAN_TOL).mean() >= SCAN_FRAC
+        assert np.isfinite(g['state'][:M]).all()
+    for e in range(M, N):                                   # the poisoned cars stay poisoned; nothing else happened
+        assert not np.isfinite(g['state'][e, 0]).all(), e
+
+
 def test_known_answer_dynamics_on_device():
     """The reference's stiff high-speed test state (dynamic_models.py:262-266, CommonRoad vehicle-2 params
     :232-253) through ONE Euler step of the device kernel: x1 == x0 + dt * f(x0, u) with f from the oracle,
