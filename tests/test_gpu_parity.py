@@ -536,6 +536,48 @@ def test_gap_follow_kernel_bit_exact():
     assert np.array_equal(a[N:, 1], ref)
 
 
+def test_consumers_survive_non_finite_inputs():
+    """The observation of a poisoned car (NaN pose, NaN/inf beams) goes through the gap-follow and reward kernels without
+    a fault, and the rows next to it come out exactly as they do without it."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import ShapedReward, gap_follow_actions
+    from tests.test_oracle_golden import REWARD_KW
+    g, r = H.load('gap_follow'), H.load('reward')
+    scans = g['scans'][:64].copy()
+    bad = scans.copy()
+    bad[5] = np.nan
+    bad[9, 100:300] = np.inf
+    bad[11, ::7] = -np.inf
+    out = []
+    for arr in (scans, bad):
+        t = torch.zeros((64, 2, 1080), dtype=torch.float32, device='cuda')
+        t[:, 1] = torch.from_numpy(arr).cuda()
+        act = torch.zeros((64, 2, 2), dtype=torch.float32, device='cuda')
+        gap_follow_actions(t, act, agent_idx=1)
+        torch.cuda.synchronize()
+        out.append(act.cpu().numpy())
+    keep = np.ones(64, bool); keep[[5, 9, 11]] = False
+    assert np.array_equal(out[0][keep], out[1][keep])
+
+    obs = r['obs'][:8].copy()
+    badobs = obs.copy()
+    badobs[2, 1080:1083] = np.nan          # pose
+    badobs[3, :1080] = np.nan              # lidar
+    badobs[4, 1080] = np.inf
+    res = []
+    for arr in (obs, badobs):
+        rw = ShapedReward(8, r['centerline'], **REWARD_KW)
+        mask = torch.ones(8, dtype=torch.uint8, device='cuda')
+        for _ in range(3):
+            got = rw(torch.from_numpy(arr).cuda(), mask)
+            mask = torch.zeros(8, dtype=torch.uint8, device='cuda')
+        torch.cuda.synchronize()
+        res.append(got.cpu().numpy())
+        rw.close()
+    keep = np.ones(8, bool); keep[[2, 3, 4]] = False
+    assert np.array_equal(res[0][keep], res[1][keep])
+
+
 def test_device_rollout_runs_without_host_sync():
     torch = _torch()
     from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout, F110VecEnv
