@@ -224,6 +224,47 @@ def test_batched_vs_oracle(num_envs, num_agents):
     assert stats['outl'] <= (1 - SCAN_FRAC) * stats['beams']
 
 
+@pytest.mark.parametrize("kw", [
+    dict(theta_dis=360, eps=1e-3, max_range=12.0, lidar_dist=0.3, timestep=0.02, ttc_thresh=0.01),
+    dict(theta_dis=4001, integrator=2, ego_idx=1, max_range=45.0, lidar_dist=-0.1),       # Euler (Integrator.Euler == 2); ego = the second car
+])
+def test_constructor_parameters_vs_oracle(kw):
+    """Every Simulator / ScanSimulator2D constructor parameter away from its default (base_classes.py:478-510,
+    laser_models.py:356-381): table size, march threshold and range, lidar offset, time step, integrator, ego index."""
+    _torch()
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+    from oracle.f110_oracle import Oracle
+    N, A = 24, 2
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    rng = np.random.default_rng(31)
+    idx = rng.integers(0, len(cl), size=N)
+    poses = np.stack([cl[idx], cl[(idx + 25) % len(cl)]], axis=1)
+    sim = BatchSim(N, A, outputs=ALL_OUTPUTS, noise_std=0.0, **kw)
+    orc = Oracle(N, A, **kw)
+    sim.set_map_arrays(*m); orc.set_map_arrays(*m)
+    worst, outl, beams = 0.0, 0, 0
+    for t in range(80):
+        noise = rng.normal(0, 0.01, size=(N, A, 1080))
+        if t == 0:
+            g = sim.reset(poses, noise); c = orc.reset(poses, noise)
+        else:
+            act = rng.uniform([-0.4189, 0], [0.4189, 10], size=(N, A, 2)).astype(np.float32)
+            g = sim.step(act, noise); c = orc.step(act, noise)
+        torch.cuda.synchronize()
+        g = {k: v.cpu().numpy() for k, v in g.items()}
+        for k in ('collisions', 'terminated', 'toggles'):
+            assert np.array_equal(g[k], c[k]), (k, t)
+        worst = max(worst, np.abs(g['state'] - c['state']).max())
+        ds = np.abs(g['scans_f64'] - c['scans'])
+        outl += int((ds > SCAN_TOL).sum()); beams += ds.size
+        assert np.abs(g['time'] - c['time']).max() <= 1e-12
+    print('constructor parameters', kw, 'state', worst, 'lidar outliers', outl, '/', beams)
+    assert worst <= STATE_TOL and outl <= (1 - SCAN_FRAC) * beams
+    sim.close()
+
+
 def test_non_finite_actions():
     """NaN / inf commands.  A NaN steer is swallowed by pid (its comparison is false) and an infinite speed by the
     acceleration clip: both match the oracle (and the reference, probed in the build container) to the usual
