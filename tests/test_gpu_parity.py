@@ -265,6 +265,43 @@ def test_constructor_parameters_vs_oracle(kw):
     sim.close()
 
 
+def test_per_agent_params_vs_oracle():
+    """update_params on one agent (heavier, longer, wider car; the oracle is pinned to the reference for this in
+    test_reference_differential): dynamics and ray-cast use the agent's parameters, GJK the Simulator's."""
+    from oracle.f110_oracle import DEFAULT_PARAMS
+    N, A = 16, 3
+    p1 = dict(DEFAULT_PARAMS)
+    p1.update(m=5.1, I=0.09, lf=0.17, lr=0.19, length=0.9, width=0.5, mu=0.8, a_max=6.0, v_max=12.0, sv_max=2.0)
+    p2 = dict(DEFAULT_PARAMS)
+    p2.update(length=0.4, width=0.2, C_Sf=5.0, C_Sr=5.5, h=0.05, s_max=0.3, s_min=-0.3)
+    be = GpuBackend(N, A, 'Shanghai_map')
+    orc = make_oracle(N, A, 'Shanghai_map')
+    be.sim.update_params(p1, 1); orc.update_params(p1, 1)
+    be.sim.update_params(p2, 2); orc.update_params(p2, 2)
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    rng = np.random.default_rng(77)
+    idx = rng.integers(0, len(cl), size=N)
+    poses = np.stack([cl[idx], cl[(idx + 14) % len(cl)], cl[(idx + 30) % len(cl)]], axis=1)
+    poses[:, 1, 1] += 0.2
+    worst, outl, beams, coll = 0.0, 0, 0, 0
+    for t in range(150):
+        noise = rng.normal(0, 0.01, size=(N, A, 1080))
+        if t == 0:
+            g = be.reset(poses, noise); c = orc.reset(poses, noise)
+        else:
+            act = rng.uniform([-0.4189, 0], [0.4189, 7], size=(N, A, 2)).astype(np.float32)
+            act[:, 0, 1] += 3.0                      # the ego is faster: it runs into the car ahead
+            g = be.step(act, noise); c = orc.step(act, noise)
+        for k in ('collisions', 'terminated', 'toggles'):
+            assert np.array_equal(g[k], c[k]), (k, t)
+        worst = max(worst, np.abs(g['state'] - c['state']).max())
+        ds = np.abs(g['scans'] - c['scans'])
+        outl += int((ds > SCAN_TOL).sum()); beams += ds.size
+        coll += int(c['collisions'].sum())
+    print('per-agent params: state', worst, 'lidar outliers', outl, '/', beams, 'collision flags', coll)
+    assert worst <= STATE_TOL and outl <= (1 - SCAN_FRAC) * beams and coll > 0
+
+
 def test_non_finite_actions():
     """NaN / inf commands.  A NaN steer is swallowed by pid (its comparison is false) and an infinite speed by the
     acceleration clip: both match the oracle (and the reference, probed in the build container) to the usual

@@ -52,6 +52,40 @@ def test_random_rollout_oracle_vs_live_reference(ref, seed):
         assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
 
 
+def test_per_agent_params_oracle_vs_live_reference(ref):
+    """Simulator.update_params(params, agent_idx) (base_classes.py:529-547): a heavier, longer, wider second car.  Dynamics
+    use the agent's own parameters, its ray-cast the agent's own length/width (:223), GJK the Simulator's (:556-560)."""
+    from oracle.f110_oracle import DEFAULT_PARAMS, Oracle
+    poses = np.array([[0., 0., 0.], [1.2, 0.25, 0.1]])
+    p1 = dict(DEFAULT_PARAMS)
+    p1.update(m=5.1, I=0.09, lf=0.17, lr=0.19, length=0.9, width=0.5, mu=0.8, a_max=6.0, v_max=12.0, sv_max=2.0)
+    fresh_statics(ref)
+    env = ref.F110Env(map_dir=REF_MAPS, map='Shanghai_map', map_ext='.png', num_agents=2)
+    env.update_params(p1, index=1)
+    o = Oracle(1, 2)
+    o.set_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+    o.update_params(p1, 1)
+    noise, rng = np.random.default_rng(42), np.random.default_rng(5)
+    obs, info = env.reset(options=poses)
+    nz = noise.normal(0., 0.01, size=1080)
+    out = o.reset(poses[None], noise=np.stack([nz, nz])[None])
+    assert np.array_equal(obs, out['obs'][0])
+    collided = False
+    for t in range(150):
+        act = rng.uniform([-0.4189, 0], [0.4189, 6], size=(2, 2)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(act)
+        nz = noise.normal(0., 0.01, size=1080)
+        out = o.step(act[None], noise=np.stack([nz, nz])[None])
+        st = np.stack([a.state for a in env.sim.agents])
+        assert np.array_equal(st, out['state'][0]) and np.array_equal(obs, out['obs'][0]), t
+        assert bool(out['terminated'][0]) == term and np.array_equal(info['collisions'], out['collisions'][0]), t
+        assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
+        collided = collided or bool(info['collisions'].any())
+        if term:
+            break
+    assert collided          # the two cars start 1.2 m apart: the run ends in a GJK collision
+
+
 def test_gap_follow_and_reward_vs_live_reference(ref):
     from oracle.f110_oracle import RewardOracle, gap_follow_action
     sys.path.insert(0, os.path.join(os.path.dirname(REF_MAPS.rstrip('/'))))
