@@ -393,6 +393,27 @@ int f110_sim_reset(F110Sim* sim, const double* poses, int32_t num_poses, const u
     return F110_OK;
 }
 
+int f110_sim_reset_host(F110Sim* sim, const double* poses, int32_t num_poses, const uint8_t* env_mask) {
+    if (!sim || !poses) return fail(F110_ERR_INVALID, "null argument");
+    if (num_poses != sim->cfg.num_agents) return fail(F110_ERR_POSE_COUNT, "Number of poses for reset does not match number of agents.");
+    Guard g(sim->cfg.device);
+    const size_t N = sim->c.N, NA = sim->c.NA;
+    double* d_poses = nullptr;
+    CUDA_TRY(cudaMalloc(&d_poses, NA * 3 * sizeof(double) + N));
+    uint8_t* d_mask = env_mask ? reinterpret_cast<uint8_t*>(d_poses + NA * 3) : nullptr;
+    cudaStream_t s = sim->host_stream;
+    cudaError_t e = cudaMemcpyAsync(d_poses, poses, NA * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && env_mask) e = cudaMemcpyAsync(d_mask, env_mask, N, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        launch_sim_reset(sim->c, sim->st, d_poses, d_mask, s);
+        sim->launches += 1;
+        e = cudaStreamSynchronize(s);
+    }
+    cudaFree(d_poses);
+    if (e != cudaSuccess) return fail(F110_ERR_CUDA, "f110_sim_reset_host: %s", cudaGetErrorString(e));
+    return F110_OK;
+}
+
 int f110_step(F110Sim* sim, const F110StepIO* io, void* stream) {
     const int rc = check_step_io(sim, io);
     if (rc != F110_OK) return rc;

@@ -156,6 +156,9 @@ int f110_set_params(F110Sim* sim, const double* params, int32_t agent_idx);
 /* Simulator.reset: poses DEVICE [N][A][3]; num_poses must equal A (else F110_ERR_POSE_COUNT);
  * env_mask DEVICE [N] or NULL.  Does not step. */
 int f110_sim_reset(F110Sim* sim, const double* poses, int32_t num_poses, const uint8_t* env_mask, void* stream);
+/* The same with HOST pointers: copies, resets on the internal stream and synchronises it (for callers without device
+ * memory of their own, e.g. the ctypes Simulator of INTEGRATION.md). */
+int f110_sim_reset_host(F110Sim* sim, const double* poses, int32_t num_poses, const uint8_t* env_mask);
 
 int f110_step(F110Sim* sim, const F110StepIO* io, void* stream);
 

@@ -1,37 +1,3 @@
-# INTEGRATION — binding the reference to `libf110_b200.so`
-
-The reference has no FFI of its own: `F110Env` (`f110_gymnasium/gym/f110_gym/envs/f110_env.py`) owns a Python
-`Simulator` (`base_classes.py:464-643`) whose methods call numba kernels.  The native boundary is therefore the
-`Simulator` class: everything below it (RaceCar, ScanSimulator2D, the four `*_models.py`) is replaced by the C ABI in
-`include/f110_b200.h`; everything above it (`F110Env`, `train_ddpg.py`, the ROS bridge) stays as it is.
-
-## Entry points and what they replace
-
-| C ABI (`include/f110_b200.h`) | reference interface replaced |
-|---|---|
-| `f110_create` / `f110_destroy` | `Simulator.__init__` (`base_classes.py:478-510`), `ScanSimulator2D.__init__` (`laser_models.py:360-381`) |
-| `f110_set_map` | `Simulator.set_map` → `ScanSimulator2D.set_map` (`base_classes.py:512-524`, `laser_models.py:383-427`); the EDT stays on the host (scipy) |
-| `f110_set_tables`, `f110_set_beam_tables` | sin/cos tables (`laser_models.py:379-381`), `RaceCar` class statics (`base_classes.py:118-158`) |
-| `f110_set_params` | `Simulator.update_params` (`base_classes.py:527-547`) |
-| `f110_sim_reset` (device pointers) / `f110_sim_reset_host` | `Simulator.reset` (`base_classes.py:627-643`) |
-| `f110_step` / `f110_step_host` (+`_async`, `f110_host_sync`) | `Simulator.step` (`base_classes.py:566-625`) **and** the post-step part of `F110Env.step` (`f110_env.py:389-421`); with `reset_mask`: `F110Env.reset` (`:425-472`) |
-| `f110_set_map_image` / `f110_get_map` | the same `set_map`, with `get_dt` (`laser_models.py:40-53`, scipy EDT) done on the device from the binarised image; bit-identical map |
-| `f110_step_host_multi` | (new) one call stepping several handles (env shards) with host buffers, PCIe copies of one shard overlapping kernels of another |
-| `f110_gap_follow` | `gap_follow_action` (`rl_training/utils/gap_follow.py:43-58`), the opponent of `train_ddpg.py:168` |
-| `f110_reward_create` / `_compute` / `_destroy` | `CenterlineSafetyProgressReward` (`rl_training/utils/rewards.py:185-355`) over `CenterlineProgress` (`rl_training/utils/track_progress.py`), `train_ddpg.py:127-145,179` |
-| `f110_get_state` / `f110_set_state` | (new) env checkpoint; the reference has none |
-| `f110_get_stats` | (new) episode counters for the cross-GPU all-reduce |
-| `f110_set_kernel_timing` / `f110_get_kernel_timing`, `f110_get_lookup_count`, `f110_gather_probe`, `f110_kernel_launches` | (new) measurement hooks used by `bench.py` (per-kernel CUDA-event times, L̄, the empirical gather roofline, launch count) |
-
-## The stub a maintainer of the reference would add
-
-`integration/native_simulator.py` — a drop-in `Simulator` for `f110_gym/envs/base_classes.py`, ctypes and numpy only (no
-torch, nothing from this repository's Python package): the C ABI is the whole interface.  It is complete and tested: on a
-B200 `tests/test_gpu_parity.py::test_integration_stub_simulator` replays the reference's recorded Simulator rollout through
-it and checks the reference's exceptions.  (`f110_gymnasium_ros2_jazzy_b200/simulator.py` is the same thing on top of
-`BatchSim`, with pinned block buffers for speed.)  The file, verbatim:
-
-```python
 """The reference-side binding: a drop-in `Simulator` for f110_gym/envs/base_classes.py backed by libf110_b200.so.
 
 This is the file a maintainer of the reference would add as f110_gym/envs/native_simulator.py and import from
@@ -152,48 +118,3 @@ class Simulator(object):
         return {'ego_idx': self.ego_idx, 'scans': list(sc), 'poses_x': list(st[:, 0]), 'poses_y': list(st[:, 1]),
                 'poses_theta': list(st[:, 4]), 'linear_vels_x': list(st[:, 3]), 'linear_vels_y': [0.] * A,
                 'ang_vels_z': list(st[:, 5]), 'collisions': self.collisions}
-```
-
-In `f110_env.py` the change is one import (`Simulator` from `f110_gym.envs.native_simulator` instead of
-`f110_gym.envs.base_classes`, `f110_env.py:34`; `Integrator` stays where it is); everything else in `F110Env` runs as written.
-
-`F110Env.step`'s own post-processing (`_check_done`, `_pack_flat_obs`, `_build_info`) can stay in Python on top of
-that dict, or be taken from the same call by also passing `obs`, `terminated`, `toggles`, `lap_times`, `lap_counts`,
-`time` in the `IO` struct — the library computes them in the same launch.
-
-## Batched / zero-copy use (what the RL loop consumes)
-
-```python
-from f110_gymnasium_ros2_jazzy_b200 import F110VecEnv
-env = F110VecEnv(4096, map_dir='rl_training/maps/', map='Shanghai_map', num_agents=2)     # torch CUDA tensors
-obs, info = env.reset(start_poses)                     # [4096, 1088] f32 on the GPU, no copy
-obs, reward, terminated, truncated, info = env.step(actions_cuda)   # actor(obs) -> actions stays on the device
-```
-
-Every output is a persistent CUDA tensor whose `data_ptr()` was handed to `f110_step`; nothing crosses PCIe.  A step
-neither allocates nor synchronises, so it can be captured by `torch.cuda.graph` (tested).  For host-side consumers
-(`train_ddpg.py`'s numpy loop) use `F110HostVecEnv`, which pipelines the PCIe copies of env chunks against the kernels
-of other chunks.  Its `send(k, actions)` / `recv(k)` pair steps one chunk at a time without waiting for the others
-(EnvPool-style): per chunk `recv -> policy -> send`, so a chunk's policy work and upload overlap the other chunks'
-kernels and downloads across step boundaries (1.19e7 env-steps/s against 9.0e6 for the synchronous `step()`).
-
-## The training loop of `train_ddpg.py` without host round trips
-
-```python
-from f110_gymnasium_ros2_jazzy_b200 import F110VecEnv, DeviceRollout, ShapedReward, Actor
-env = F110VecEnv(8192, map_dir=..., map='Shanghai_map', num_agents=2, outputs=('obs', 'reward', 'terminated', 'scans_f32'))
-reward_fn = ShapedReward(8192, centerline_csv_rows, w_prog=5.0, alive_bonus=0.5, ...)   # train_ddpg.py:127-145
-loop = DeviceRollout(env, actor, opponent='gap_follow', reward_fn=reward_fn)          # train_ddpg.py:160-202 per step
-obs = loop.reset(start_poses)
-obs, reward, terminated, truncated, info = loop.step()     # actor -> gap-follow kernel -> step kernels -> reward kernel
-```
-
-## Errors, ownership, threading
-
-Status codes map onto the reference's exceptions (`_lib.check`): `F110_ERR_MAP_NOT_SET` → `ValueError('Map is not set
-for scan simulator.')` (`laser_models.py:445-446`), `F110_ERR_POSE_COUNT` → `ValueError` (`base_classes.py:638-639`),
-`F110_ERR_INDEX` → `IndexError` (`base_classes.py:547`), `F110_ERR_INTEGRATOR` → `SyntaxError` (`base_classes.py:399`).
-All I/O buffers belong to the caller; the library owns only its arena.  A handle is bound to one device and one
-calling thread at a time; the device-pointer path (`f110_step`, caller's stream) and the host-buffer path
-(`f110_step_host*`, the handle's own stream) must not be in flight on the same handle at once.  There is no CPU fallback: without a CUDA device `f110_create` returns
-`F110_ERR_NO_DEVICE`, and the Python package raises at construction.

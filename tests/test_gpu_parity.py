@@ -6,6 +6,8 @@
 Tolerances are BASELINE.json's north_star: collision / done / lap flags bit-exact over the rollout, fp64
 vehicle state within 1e-9 absolute, lidar within 1e-6 m on >= 99.9 % of beams (outliers counted).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -175,6 +177,43 @@ def test_c1_single_agent_sim_rollout():
             assert (np.abs(out['scans'][0, 0] - g['scans'][t // int(g['every'])]) <= SCAN_TOL).mean() >= SCAN_FRAC
     assert worst <= STATE_TOL
     print('c1 worst state diff', worst)
+
+
+def test_integration_stub_simulator(tmp_path):
+    """integration/native_simulator.py -- the ctypes-only `Simulator` INTEGRATION.md hands to a maintainer of the
+    reference -- replays the reference's recorded single-agent Simulator rollout (golden C1) and raises the reference's
+    exceptions.  It imports nothing from this package: the C ABI is the whole interface."""
+    import importlib.util
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    from f110_gymnasium_ros2_jazzy_b200.params import default_params
+    _torch()
+    os.environ.setdefault('F110_B200_LIB', _lib.LIB_PATH)
+    spec = importlib.util.spec_from_file_location(
+        'native_simulator', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'integration', 'native_simulator.py'))
+    ns = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ns)
+    map_dir, name = H.write_map_files('Shanghai_map', str(tmp_path))
+    g = H.load('rollout_c1_single')
+    sim = ns.Simulator(default_params(), 1, int(g['seed']))
+    with pytest.raises(ValueError, match='Map is not set'):
+        sim.reset(g['pose'][None]); sim.step(g['action'])
+    sim.set_map(map_dir + name + '.yaml', '.png')
+    with pytest.raises(ValueError, match='Number of poses'):
+        sim.reset(np.zeros((2, 3)))
+    with pytest.raises(IndexError):
+        sim.update_params(default_params(), agent_idx=3)
+    worst = 0.0
+    for t in range(600):
+        if g['resets'][t] or t == 0:
+            sim.reset(g['pose'][None])
+        obs = sim.step(g['action'])
+        st = np.array([obs['poses_x'][0], obs['poses_y'][0], obs['poses_theta'][0], obs['linear_vels_x'][0], obs['ang_vels_z'][0]])
+        worst = max(worst, np.abs(st - g['state'][t][[0, 1, 4, 3, 5]]).max())
+        assert obs['collisions'][0] == g['collisions'][t], t
+        if t % int(g['every']) == 0:
+            assert (np.abs(obs['scans'][0] - g['scans'][t // int(g['every'])]) <= SCAN_TOL).mean() >= SCAN_FRAC
+    assert worst <= STATE_TOL
+    print('integration stub: worst state diff', worst)
 
 
 # ----------------------------------------------------------------------------- oracle on seeded batches
