@@ -12,7 +12,7 @@ from .env import F110Env, F110HostVecEnv, F110VecEnv
 from .backend import ALL_OUTPUTS, FAST_OUTPUTS, BatchSim
 from .params import default_params
 from .dist import EpisodeStats, shard_range
-from .rollout import Actor, DeviceRollout, ShapedReward, gap_follow_actions
+from .rollout import Actor, DeviceReplayBuffer, DeviceRollout, ShapedReward, gap_follow_actions
 
 # same id the reference registers (f110_gym/__init__.py:2-5)
 try:
@@ -21,4 +21,4 @@ except Exception:  # already registered
     pass
 
 __all__ = ['F110Env', 'F110VecEnv', 'F110HostVecEnv', 'Simulator', 'Integrator', 'BatchSim', 'make', 'default_params', 'shard_range',
-           'EpisodeStats', 'Actor', 'DeviceRollout', 'ShapedReward', 'gap_follow_actions', 'ALL_OUTPUTS', 'FAST_OUTPUTS', 'HAVE_GYMNASIUM']
+           'EpisodeStats', 'Actor', 'DeviceReplayBuffer', 'DeviceRollout', 'ShapedReward', 'gap_follow_actions', 'ALL_OUTPUTS', 'FAST_OUTPUTS', 'HAVE_GYMNASIUM']

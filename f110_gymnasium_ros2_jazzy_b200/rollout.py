@@ -61,11 +61,12 @@ class DeviceRollout(object):
     """ego = policy(obs), opponent = gap-follow on its own scan, env.step -- no host round trip per step.
 
     ``reward_fn`` (optional, e.g. ShapedReward) replaces the env's constant reward, as train_ddpg.py:179 does.
+    ``replay`` (optional, e.g. DeviceReplayBuffer) receives every transition (obs, ego action, reward, next obs, done).
     ``env`` is an F110VecEnv with num_agents == 2 and 'scans_f32' among its outputs; ``policy`` maps the observation
     tensor [N, B+8] to ego actions [N, 2] (e.g. Actor).  ``opponent`` may be 'gap_follow' or a constant (steer, speed).
     """
 
-    def __init__(self, env, policy, opponent='gap_follow', reward_fn=None):
+    def __init__(self, env, policy, opponent='gap_follow', reward_fn=None, replay=None):
         if env.num_agents != 2:
             raise ValueError("DeviceRollout mirrors the reference's two-car loop (ego + opponent)")
         if opponent == 'gap_follow' and 'scans_f32' not in env.backend.out:
@@ -78,6 +79,9 @@ class DeviceRollout(object):
         self.obs = None
         self.reward_fn = reward_fn          # e.g. ShapedReward: train_ddpg.py:179 discards the env's reward for it
         self.reward = None
+        self.replay = replay                # e.g. DeviceReplayBuffer: agent.remember(obs, ego_action, r, next_obs, done), :185
+        self._prev_obs = None if replay is None else torch.zeros((env.num_envs,) + tuple(env.single_observation_shape),
+                                                                 dtype=torch.float32, device=env.device)
 
     def reset(self, poses):
         self.obs, o = self.env.reset(poses)
@@ -92,11 +96,97 @@ class DeviceRollout(object):
         if self.reward_fn is not None:
             # an env that terminated on the previous step is auto-reset by this one: its reward object starts over too
             self._fresh.copy_(self.env.backend.out['terminated'])
+        if self.replay is not None:
+            self._prev_obs.copy_(self.obs)          # the env rewrites its observation tensor in place
         self.obs, reward, terminated, truncated, info = self.env.step(self.actions)
         if self.reward_fn is not None:
             reward = self.reward_fn(self.obs, self._fresh)
         self.reward = reward
+        if self.replay is not None:
+            self.replay.add(self._prev_obs, self.actions[:, 0, :], reward, self.obs, terminated)
         return self.obs, reward, terminated, truncated, info
+
+
+class DeviceReplayBuffer(object):
+    """The replay memory of the reference's DDPG agent (rl_training/DDPG/replay_buffer.py:6-135,
+    PrioritizedExperienceReplayBuffer) as device-resident tensors, filled a whole batch of envs at a time, so that
+    transitions go from the env's output tensors into the buffer without touching the host.
+
+    Same semantics: ring-buffer insertion (:46-71) with a new transition's priority = the current maximum (1.0 when
+    empty); sampling probabilities (prio + eps)^alpha / sum (:86-95), without replacement when the buffer holds at
+    least a batch (:97-101); importance weights (len * p)^-beta normalised by their maximum (:103-113);
+    update_priorities clamps to [1e-8, f32 max] and maps non-finite values to 1e-6 (:120-135).
+    Layout: SoA tensors [capacity, ...] (obs and next_obs f32 [capacity, obs_dim]: 8.7 KB per transition at 1088).
+    """
+
+    def __init__(self, capacity, batch_size, obs_dim=1088, act_dim=2, alpha=0.6, priority_epsilon=1e-6, device=None, seed=42):
+        assert capacity > 0 and batch_size > 0
+        self.capacity, self.batch_size, self.alpha, self.eps = int(capacity), int(batch_size), float(alpha), float(priority_epsilon)
+        dev = torch.device(device) if device is not None else torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        self.device = dev
+        self.obs = torch.zeros((capacity, obs_dim), dtype=torch.float32, device=dev)
+        self.next_obs = torch.zeros((capacity, obs_dim), dtype=torch.float32, device=dev)
+        self.action = torch.zeros((capacity, act_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(capacity, dtype=torch.uint8, device=dev)
+        self.priority = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.length, self.next_idx = 0, 0
+        self._max_prio = torch.ones((), dtype=torch.float32, device=dev)     # running maximum, kept on the device
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+
+    def __len__(self):
+        return self.length
+
+    @torch.no_grad()
+    def add(self, obs, action, reward, next_obs, done, priority=None):
+        """One transition per env: obs/next_obs [n, obs_dim], action [n, act_dim], reward [n], done [n]."""
+        n = obs.shape[0]
+        if n > self.capacity:
+            raise ValueError("more transitions in one add() than the buffer holds")
+        idx = (self.next_idx + torch.arange(n, device=self.device)) % self.capacity
+        if priority is None:
+            p0 = self._max_prio.expand(n) if self.length > 0 else torch.ones(n, dtype=torch.float32, device=self.device)
+        else:
+            p0 = torch.as_tensor(priority, dtype=torch.float32, device=self.device).expand(n)
+        p0 = torch.clamp(p0, 1e-8, torch.finfo(torch.float32).max)
+        self.obs.index_copy_(0, idx, obs.to(torch.float32))
+        self.next_obs.index_copy_(0, idx, next_obs.to(torch.float32))
+        self.action.index_copy_(0, idx, action.to(torch.float32))
+        self.reward.index_copy_(0, idx, reward.to(torch.float32).reshape(n))
+        self.done.index_copy_(0, idx, done.to(torch.uint8).reshape(n))
+        self.priority.index_copy_(0, idx, p0)
+        self._max_prio = torch.maximum(self._max_prio, p0.max()) if self.length > 0 else p0.max()
+        self.length = min(self.length + n, self.capacity)
+        self.next_idx = (self.next_idx + n) % self.capacity
+
+    def probabilities(self):
+        ps = (self.priority[:self.length] + self.eps).double() ** self.alpha     # the sum is formed in float32, as numpy does (:88)
+        den = ps.sum()
+        if not bool(torch.isfinite(den)) or float(den) <= 0.0:
+            return torch.full((self.length,), 1.0 / self.length, dtype=torch.float64, device=self.device)
+        return ps / den
+
+    @torch.no_grad()
+    def sample(self, beta=0.4):
+        """-> idxs [B] int64, (obs, action, reward, next_obs, done) gathered on the device, weights [B] f32."""
+        if self.length == 0:
+            raise ValueError("Cannot sample from an empty buffer.")
+        probs = self.probabilities()
+        idxs = torch.multinomial(probs, self.batch_size, replacement=self.length < self.batch_size, generator=self.gen)
+        w = (self.length * probs[idxs]) ** (-float(beta))
+        m = w.max()
+        w = torch.ones_like(w) if (not bool(torch.isfinite(m)) or float(m) <= 0.0) else w / m
+        batch = (self.obs[idxs], self.action[idxs], self.reward[idxs], self.next_obs[idxs], self.done[idxs])
+        return idxs, batch, w.to(torch.float32)
+
+    @torch.no_grad()
+    def update_priorities(self, idxs, priorities):
+        pr = torch.as_tensor(priorities, dtype=torch.float32, device=self.device).reshape(-1)
+        pr = torch.clamp(pr, 1e-8, torch.finfo(torch.float32).max)
+        pr = torch.where(torch.isfinite(pr), pr, torch.full_like(pr, 1e-6))
+        self.priority.index_copy_(0, torch.as_tensor(idxs, device=self.device).reshape(-1).long(), pr)
+        self._max_prio = self.priority[:self.length].max()
 
 
 # CenterlineSafetyProgressReward.__init__ defaults (rl_training/utils/rewards.py:196-222)

@@ -719,6 +719,41 @@ def test_device_rollout_runs_without_host_sync():
     env.close()
 
 
+def test_device_rollout_fills_device_replay_buffer():
+    """DeviceRollout(replay=DeviceReplayBuffer): every transition lands in the device buffer in env order --
+    (obs before the step, the ego action that was applied, reward, obs after, done) -- and a prioritised batch can be
+    drawn, all without a host copy (train_ddpg.py:160-188's remember / replay shape)."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceReplayBuffer, DeviceRollout, F110VecEnv
+    N, T = 32, 12
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
+    poses = np.stack([cl[idx], cl[(idx + 40) % len(cl)]], axis=1)
+    env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'scans_f32'))
+    torch.manual_seed(1)
+    actor = Actor(1088, 2, [-0.4189, 0.0], [0.4189, 20.0]).cuda()
+    buf = DeviceReplayBuffer(capacity=N * T, batch_size=64, device='cuda')
+    ro = DeviceRollout(env, actor, replay=buf)
+    obs0 = ro.reset(poses).clone()
+    seen = []
+    for t in range(T):
+        before = ro.obs.clone()
+        obs, r, term, trunc, info = ro.step()
+        seen.append((before, ro.actions[:, 0].clone(), r.clone(), obs.clone(), term.clone()))
+    torch.cuda.synchronize()
+    assert len(buf) == N * T and buf.next_idx == 0 and buf.obs.is_cuda
+    for t, (o, a, r, no, d) in enumerate(seen):
+        sl = slice(t * N, (t + 1) * N)
+        assert torch.equal(buf.obs[sl], o) and torch.equal(buf.next_obs[sl], no) and torch.equal(buf.action[sl], a)
+        assert torch.equal(buf.reward[sl], r) and torch.equal(buf.done[sl], d)
+    assert torch.equal(buf.obs[:N], obs0)
+    idxs, (o, a, r, no, d), w = buf.sample(beta=0.4)
+    assert o.shape == (64, 1088) and w.is_cuda and float(w.max()) == 1.0 and len(set(idxs.tolist())) == 64
+    buf.update_priorities(idxs, torch.rand(64, device='cuda') + 0.1)
+    env.close()
+
+
 def test_c4_full_size_sharded_properties():
     """BASELINE config 4 size: 262 144 envs on one handle (the 1-GPU end of the sweep).  Replicated start poses must
     give replicated results across the whole batch (index arithmetic survives 2.8e8 rays), outputs stay in range,

@@ -178,3 +178,38 @@ def test_bind_host_to_gpu_uses_the_gpus_numa_node(tmp_path):
         assert bind_host_to_gpu(0, pci_bus_id="0000:ff:00.0", sysfs=str(tmp_path)) is None
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_device_replay_buffer_ring_and_per_formulas():
+    """DeviceReplayBuffer (torch tensors, here on the CPU) against the reference's PrioritizedExperienceReplayBuffer
+    formulas (rl_training/DDPG/replay_buffer.py:46-135): ring insertion, new-transition priority = current max,
+    sampling probabilities, importance weights, priority clamping."""
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200.rollout import DeviceReplayBuffer
+    buf = DeviceReplayBuffer(capacity=10, batch_size=4, obs_dim=3, act_dim=2, alpha=0.6, device='cpu', seed=1)
+    def batch(n, base):
+        o = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) + base
+        return o, torch.ones(n, 2) * base, torch.full((n,), float(base)), o + 0.5, torch.zeros(n, dtype=torch.uint8)
+    buf.add(*batch(4, 100))
+    assert len(buf) == 4 and buf.next_idx == 4 and torch.all(buf.priority[:4] == 1.0)
+    buf.update_priorities([1, 2], [5.0, float('nan')])
+    assert buf.priority[1] == 5.0 and abs(float(buf.priority[2]) - 1e-6) < 1e-12
+    buf.add(*batch(8, 200))                                  # wraps: slots 4..9 then 0..1
+    assert len(buf) == 10 and buf.next_idx == 2
+    assert torch.all(buf.priority[4:10] == 5.0) and torch.all(buf.priority[0:2] == 5.0)    # new ones get the running max
+    assert float(buf.reward[0]) == 200.0 and float(buf.reward[3]) == 100.0
+    # probabilities and weights, restated in numpy exactly as the reference computes them
+    ps = buf.priority[:10].numpy().astype(np.float32)
+    pa = np.power(ps + 1e-6, 0.6, dtype=np.float64)
+    want = pa / pa.sum()
+    assert np.allclose(buf.probabilities().numpy(), want, rtol=1e-12, atol=0)
+    idxs, (o, a, r, no, d), w = buf.sample(beta=0.4)
+    assert len(set(idxs.tolist())) == 4                       # without replacement once a batch fits
+    wr = np.power(10 * want[idxs.numpy()], -0.4)
+    assert np.allclose(w.numpy(), (wr / wr.max()).astype(np.float32), rtol=1e-6)
+    assert torch.equal(o, buf.obs[idxs]) and torch.equal(no, buf.next_obs[idxs]) and w.dtype == torch.float32
+    small = DeviceReplayBuffer(capacity=8, batch_size=4, obs_dim=3, device='cpu')
+    with pytest.raises(ValueError):
+        small.sample()
+    small.add(*batch(2, 1))
+    assert small.sample()[0].shape == (4,)                    # fewer than a batch stored: with replacement

@@ -95,3 +95,35 @@ def test_gap_follow_and_reward_vs_live_reference(ref):
         s = rng.uniform(0, 6, 1080).astype(np.float32)
         s[rng.integers(0, 1000):][:rng.integers(1, 80)] = rng.uniform(0, 0.4)
         assert np.array_equal(gap_follow_action(s), ref_gf(s.copy()))
+
+
+def test_replay_buffer_vs_live_reference():
+    """DeviceReplayBuffer against rl_training/DDPG/replay_buffer.py on the same insert / update sequence: ring position,
+    priorities, sampling probabilities, and -- for the indices the reference drew -- the importance weights."""
+    import importlib.util
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200.rollout import DeviceReplayBuffer
+    path = os.path.join(os.path.dirname(REF_MAPS.rstrip('/')), 'DDPG', 'replay_buffer.py')
+    spec = importlib.util.spec_from_file_location('ref_replay_buffer', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = mod.PrioritizedExperienceReplayBuffer(buffer_size=50, batch_size=8, alpha=0.6, seed=3)
+    mine = DeviceReplayBuffer(capacity=50, batch_size=8, obs_dim=4, act_dim=2, alpha=0.6, device='cpu')
+    rng = np.random.default_rng(0)
+    for rnd in range(9):
+        n = 7
+        o = rng.normal(size=(n, 4)).astype(np.float32)
+        for i in range(n):
+            ref.add(('exp', rnd, i))
+        mine.add(torch.from_numpy(o), torch.zeros(n, 2), torch.zeros(n), torch.from_numpy(o), torch.zeros(n, dtype=torch.uint8))
+        assert len(ref) == len(mine) and ref._next_idx == mine.next_idx
+        idxs, _, w_ref = ref.sample(beta=0.4)
+        pr = np.abs(rng.normal(size=8)).astype(np.float32) * 3
+        pr[0] = np.inf if rnd == 4 else (np.nan if rnd == 6 else pr[0])      # clamped to f32 max / replaced by 1e-6
+        ref.update_priorities(idxs, pr)
+        mine.update_priorities(idxs, pr)
+        assert np.array_equal(ref._buffer['priority'][:len(ref)], mine.priority[:len(mine)].numpy())
+        probs = mine.probabilities().numpy()
+        idxs2, _, w_ref2 = ref.sample(beta=0.7)
+        w = np.power(len(mine) * probs[idxs2], -0.7)
+        assert np.allclose((w / w.max()).astype(np.float32), w_ref2, rtol=1e-6, atol=0)
