@@ -22,10 +22,17 @@ ap.add_argument("--reward", action="store_true", help="also evaluate the shaped 
 ap.add_argument("--graph", action="store_true", help="capture one rollout step in a CUDA graph")
 args = ap.parse_args()
 
+# under torchrun: one process per GPU, `--envs` per GPU (BASELINE config 5 = 8 x 8192), env-index sharding, no collective on
+# the step path; the max over ranks of the device time is reported
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 N = args.envs
 m = H.golden_map('Shanghai_map')
 cl = H.load('maps')['Shanghai_map__centerline_poses']
-idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
+idx = np.linspace(0, len(cl) - 1, N * world).round().astype(int)[rank * N:(rank + 1) * N]
 poses = np.stack([cl[idx], cl[(idx + 40) % len(cl)]], axis=1)
 env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'scans_f32'))
 torch.manual_seed(42)
@@ -61,6 +68,15 @@ e1.record()
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 ms = e0.elapsed_time(e1)
-print(json.dumps({"config": "C5 rollout: %d two-agent envs, actor 1088-128-128-2 + %s opponent%s%s" % (N, args.opponent, " + shaped reward" if args.reward else "", ", CUDA graph" if args.graph else ""),
-                  "env_steps_per_s": N * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+if world > 1:
+    t = torch.tensor([ms, wall], dtype=torch.float64, device='cuda')
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, wall = float(t[0]), float(t[1])
+    N = N * world
+if rank == 0:
+  print(json.dumps({"config": "C5 rollout: %d two-agent envs, actor 1088-128-128-2 + %s opponent%s%s" % (N, args.opponent, " + shaped reward" if args.reward else "", ", CUDA graph" if args.graph else ""),
+                  "n_gpus": world, "env_steps_per_s": N * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
                   "wall_ms_per_step": 1e3 * wall / args.steps, "rays_per_s": N * 2 * 1080 * args.steps / (ms * 1e-3)}))
+if world > 1:
+    dist.destroy_process_group()
