@@ -320,7 +320,8 @@ __global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restri
 // ---------------------------------------------------------------- K2: lidar
 
 // xy_2_rc + distance_transform, laser_models.py:55-104 -- the exact restatement (two IEEE divisions).
-// Kept out of line: the hot loop only comes here for the ~1e-5 of lookups that fall in the guard band.
+// Kept out of line and out of the hot loop: only the finishing loop of a ray whose lookup fell in the guard band calls it.
+// (A float->int conversion of NaN does not give 0 on this hardware -- (int)NaN is negative -- hence the two-sided clamp.)
 __device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double res, double wres, double hres, int W, int last) {
     int idx;
     if (x_rot < 0 || x_rot >= wres || y_rot < 0 || y_rot >= hres) {
@@ -339,8 +340,9 @@ __device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double 
 // quotient is < 2.3e-16 relative, i.e. < 1e-6 units since q < 2^32, and the reference's own rounded quotient is within
 // half an ulp of the true one, so whenever the F fractional bits are at least one unit away from both cell edges,
 // trunc(q) >> F is exactly the reference's int(x_rot/res) and (q < W << F) is exactly its in-map test.  Everything
-// else -- the 2/2^F of lookups next to a cell edge, the map border, negative (converts to 0), NaN (0) and huge
-// (0xFFFFFFFF) coordinates -- is not decided here: fast_cell returns false and the caller takes the exact path.
+// else -- the 2/2^F of lookups next to a cell edge, the map border, negative (converts to 0), huge (0xFFFFFFFF) and NaN
+// (0 or 0x80000000: fraction 0 either way) coordinates -- is not decided here: fast_cell returns false and the caller takes
+// the exact path.
 template <bool IDENT>
 __device__ __forceinline__ void map_frame(const MapView& m, double x, double y, double& x_rot, double& y_rot) {
     const double x_trans = x - m.ox;
