@@ -52,6 +52,43 @@ def test_random_rollout_oracle_vs_live_reference(ref, seed):
         assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
 
 
+@pytest.mark.parametrize("case", [0, 1])
+def test_env_kwargs_oracle_vs_live_reference(ref, case):
+    """F110Env constructor kwargs away from their defaults (f110_env.py:104-185): 3-4 agents, time step, Euler, lidar
+    offset, ego index, seed.  State / flat obs bit-exact, flags and time exact, scans within 1e-12."""
+    from oracle.f110_oracle import Oracle
+    kw = (dict(num_agents=3, timestep=0.02, integrator=ref.Integrator.Euler, lidar_dist=0.2, ego_idx=1, seed=7),
+          dict(num_agents=4, timestep=0.005, lidar_dist=-0.15, ego_idx=3, seed=123))[case]
+    A = kw['num_agents']
+    cl = np.loadtxt(os.path.join(os.path.dirname(REF_MAPS.rstrip('/')), 'maps/cenerlines/Shanghai_map.csv'), delimiter=',', comments='#')
+    def pose(k):
+        return [cl[k, 0], cl[k, 1], np.arctan2(cl[k + 1, 1] - cl[k, 1], cl[k + 1, 0] - cl[k, 0])]
+    fresh_statics(ref)
+    env = ref.F110Env(map_dir=REF_MAPS, map='Shanghai_map', map_ext='.png', **kw)
+    o = Oracle(1, A, timestep=kw['timestep'], integrator=getattr(kw.get('integrator', 1), 'value', 1),
+               lidar_dist=kw['lidar_dist'], ego_idx=kw['ego_idx'])
+    o.set_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+    poses = np.array([pose(1000 + 30 * a) for a in range(A)])
+    noise, rng = np.random.default_rng(kw['seed']), np.random.default_rng(1)
+    obs, info = env.reset(options=poses)
+    nz = noise.normal(0., 0.01, size=1080)
+    out = o.reset(poses[None], noise=np.stack([nz] * A)[None])
+    assert np.array_equal(obs, out['obs'][0])
+    for t in range(200):
+        act = rng.uniform([-0.4189, 0], [0.4189, 8], size=(A, 2)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(act)
+        nz = noise.normal(0., 0.01, size=1080)
+        out = o.step(act[None], noise=np.stack([nz] * A)[None])
+        st = np.stack([a.state for a in env.sim.agents])
+        assert np.array_equal(st, out['state'][0]) and np.array_equal(obs, out['obs'][0]), t
+        assert bool(out['terminated'][0]) == term and np.array_equal(info['collisions'], out['collisions'][0]), t
+        assert info['time'] == float(out['time'][0]) and np.float32(r) == out['reward'][0], t
+        assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
+        if term:
+            break
+    assert t > 50
+
+
 def test_per_agent_params_oracle_vs_live_reference(ref):
     """Simulator.update_params(params, agent_idx) (base_classes.py:529-547): a heavier, longer, wider second car.  Dynamics
     use the agent's own parameters, its ray-cast the agent's own length/width (:223), GJK the Simulator's (:556-560)."""
