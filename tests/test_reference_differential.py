@@ -89,6 +89,40 @@ def test_env_kwargs_oracle_vs_live_reference(ref, case):
     assert t > 50
 
 
+def test_update_map_mid_episode_oracle_vs_live_reference(ref):
+    """F110Env.update_map (f110_env.py:474-485) between steps: the cars keep their state, the scans come from the new map
+    (here one whose yaml origin is rotated by -pi/2)."""
+    from oracle.f110_oracle import Oracle
+    poses = np.array([[0., 0., 1.5], [0.3, 4.0, 1.5]])
+    fresh_statics(ref)
+    env = ref.F110Env(map_dir=REF_MAPS, map='Shanghai_map', map_ext='.png', num_agents=2)
+    o = Oracle(1, 2)
+    o.set_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+    noise, rng = np.random.default_rng(42), np.random.default_rng(8)
+    obs, info = env.reset(options=poses)
+    nz = noise.normal(0., 0.01, size=1080)
+    out = o.reset(poses[None], noise=np.stack([nz, nz])[None])
+    assert np.array_equal(obs, out['obs'][0])
+    for t in range(120):
+        if t == 40:
+            env.update_map(REF_MAPS + 'straight_corridor.yaml', '.png')
+            o.set_map(REF_MAPS + 'straight_corridor.yaml', '.png')
+        if t == 80:
+            env.update_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+            o.set_map(REF_MAPS + 'Shanghai_map.yaml', '.png')
+        act = rng.uniform([-0.2, 0], [0.2, 4], size=(2, 2)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(act)
+        nz = noise.normal(0., 0.01, size=1080)
+        out = o.step(act[None], noise=np.stack([nz, nz])[None])
+        st = np.stack([a.state for a in env.sim.agents])
+        assert np.array_equal(st, out['state'][0]) and np.array_equal(obs, out['obs'][0]), t
+        assert bool(out['terminated'][0]) == term and np.array_equal(info['collisions'], out['collisions'][0]), t
+        assert np.abs(np.stack(ref.F110Env.current_obs['scans']) - out['scans'][0]).max() < 1e-12
+        if term:
+            break
+    assert t >= 45          # the run got past the first map swap
+
+
 def test_per_agent_params_oracle_vs_live_reference(ref):
     """Simulator.update_params(params, agent_idx) (base_classes.py:529-547): a heavier, longer, wider second car.  Dynamics
     use the agent's own parameters, its ray-cast the agent's own length/width (:223), GJK the Simulator's (:556-560)."""
