@@ -341,6 +341,34 @@ def test_per_agent_params_vs_oracle():
     assert worst <= STATE_TOL and outl <= (1 - SCAN_FRAC) * beams and coll > 0
 
 
+def test_map_swap_between_steps_vs_oracle():
+    """f110_set_map between steps (F110Env.update_map, f110_env.py:474-485; the oracle is pinned to the reference for this):
+    state carries over, scans come from the new map -- a different size, resolution and a rotated origin -- and back."""
+    N, A = 8, 2
+    be = GpuBackend(N, A, 'Shanghai_map')
+    orc = make_oracle(N, A, 'Shanghai_map')
+    rng = np.random.default_rng(21)
+    poses = np.tile(np.array([[0., 0., 1.5], [0.3, 4.0, 1.5]]), (N, 1, 1))
+    poses[:, :, 0] += rng.uniform(-0.2, 0.2, size=(N, 1))
+    outl = beams = 0
+    for t in range(90):
+        noise = rng.normal(0, 0.01, size=(N, A, 1080))
+        if t == 30 or t == 60:
+            name = 'straight_corridor' if t == 30 else 'Shanghai_map'
+            be.sim.set_map_arrays(*H.golden_map(name)); orc.set_map_arrays(*H.golden_map(name))
+        if t == 0:
+            g = be.reset(poses, noise); c = orc.reset(poses, noise)
+        else:
+            act = rng.uniform([-0.2, 0], [0.2, 4], size=(N, A, 2)).astype(np.float32)
+            g = be.step(act, noise); c = orc.step(act, noise)
+        for k in ('collisions', 'terminated', 'toggles'):
+            assert np.array_equal(g[k], c[k]), (k, t)
+        assert np.abs(g['state'] - c['state']).max() <= STATE_TOL, t
+        ds = np.abs(g['scans'] - c['scans'])
+        outl += int((ds > SCAN_TOL).sum()); beams += ds.size
+    assert outl <= (1 - SCAN_FRAC) * beams
+
+
 def test_non_finite_actions():
     """NaN / inf commands.  A NaN steer is swallowed by pid (its comparison is false) and an infinite speed by the
     acceleration clip: both match the oracle (and the reference, probed in the build container) to the usual
