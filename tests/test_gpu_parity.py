@@ -551,16 +551,20 @@ def test_step_host_matches_device_path():
         assert np.array_equal(d[k], h[k].numpy()), k
 
 
-def test_host_vec_env_matches_device_vec_env():
-    """F110HostVecEnv (chunked f110_step_host_async pipeline) == one F110VecEnv batch, noise off, auto-reset on."""
+@pytest.mark.parametrize("A,chunks,extra", [(1, 3, ()), (2, (1, 3), ('scans_f32', 'state', 'toggles')), (2, 1, ('scans_f64',))])
+def test_host_vec_env_matches_device_vec_env(A, chunks, extra):
+    """F110HostVecEnv (chunked f110_step_host_async pipeline, block-laid-out pinned buffers, merged copies) == one F110VecEnv
+    batch, noise off, auto-reset on -- one and two cars, even and uneven chunks, with and without extra outputs."""
     torch = _torch()
-    from f110_gymnasium_ros2_jazzy_b200 import F110HostVecEnv, F110VecEnv
+    from f110_gymnasium_ros2_jazzy_b200 import FAST_OUTPUTS, F110HostVecEnv, F110VecEnv
     N = 96
     m = H.golden_map('Shanghai_map')
     cl = H.load('maps')['Shanghai_map__centerline_poses']
-    poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
-    dev = F110VecEnv(N, num_agents=1, map_arrays=m, noise_std=0.0)
-    host = F110HostVecEnv(N, chunks=3, map_arrays=m, num_agents=1, noise_std=0.0)
+    idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
+    poses = np.stack([cl[(idx + 25 * a) % len(cl)] for a in range(A)], axis=1)
+    outs = FAST_OUTPUTS + tuple(extra)
+    dev = F110VecEnv(N, num_agents=A, map_arrays=m, noise_std=0.0, outputs=outs)
+    host = F110HostVecEnv(N, chunks=chunks, map_arrays=m, num_agents=A, noise_std=0.0, outputs=outs)
     rng = np.random.default_rng(11)
     od, _ = dev.reset(poses)
     oh, _ = host.reset(poses)
@@ -568,12 +572,15 @@ def test_host_vec_env_matches_device_vec_env():
     assert np.array_equal(od.cpu().numpy(), oh)
     terms = 0
     for t in range(150):
-        act = rng.uniform([-0.4189, 0], [0.4189, 20], size=(N, 1, 2)).astype(np.float32)
-        od, rd, td, _, _ = dev.step(torch.from_numpy(act).cuda())
-        oh, rh, th, _, _ = host.step(act)
+        act = rng.uniform([-0.4189, 0], [0.4189, 20], size=(N, A, 2)).astype(np.float32)
+        od, rd, td, _, infod = dev.step(torch.from_numpy(act).cuda())
+        oh, rh, th, _, infoh = host.step(act)
         torch.cuda.synchronize()
         assert np.array_equal(td.cpu().numpy(), th), t
         assert np.array_equal(od.cpu().numpy(), oh), t
+        assert np.array_equal(rd.cpu().numpy(), rh), t
+        for k in extra:
+            assert np.array_equal(infod[k].cpu().numpy(), infoh[k].numpy()), (k, t)
         terms += int(th.sum())
     assert terms > 0      # the auto-reset path was exercised
     host.close(); dev.close()
