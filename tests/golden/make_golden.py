@@ -179,7 +179,7 @@ def main():
                         **record_env_rollout(env, [[0.0, 0.5, 1.5708], [0.3, 3.0, 1.5708]], acts))
     # ---- S5: config C1, Simulator-level single agent with resets on collision
     np.savez_compressed(os.path.join(HERE, 'rollout_c1_single.npz'),
-                        **record_sim_rollout(REF_MAPS, 'Shanghai_map', [0, 0, 0], [0.0, 2.0], 2000))
+                        **record_sim_rollout(REF_MAPS, 'Shanghai_map', [0, 0, 0], [0.0, 2.0], 10000))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
@@ -281,8 +281,95 @@ def make_rotated_scan_golden(theta=0.3):
     print('scans_rotated.npz', scans.shape, 'range', scans.min(), scans.max())
 
 
+def make_c1_golden():
+    """BASELINE config C1 at its full length: 10 000 Simulator.step calls, single agent, constant action, reset on
+    every collision -> tests/golden/rollout_c1_single.npz"""
+    np.savez_compressed(os.path.join(HERE, 'rollout_c1_single.npz'),
+                        **record_sim_rollout(REF_MAPS, 'Shanghai_map', [0, 0, 0], [0.0, 2.0], 10000))
+    print('rollout_c1_single.npz', os.path.getsize(os.path.join(HERE, 'rollout_c1_single.npz')) // 1024, 'KiB')
+
+
+def large_map_poses(name, k=1, n=64):
+    """Poses for the C4 large-map scans: n centerline poses of the Shanghai track (levine: free cells picked by a
+    seeded generator), plus poses next to and beyond the map border and one far outside."""
+    m = dict(np.load(os.path.join(HERE, 'maps.npz')))
+    if name == 'levine':
+        return None
+    cl = m['Shanghai_map__centerline_poses']
+    poses = cl[np.linspace(0, len(cl) - 1, n).round().astype(int)].copy()
+    o, res, (h, w) = m['Shanghai_map__origin'], float(m['Shanghai_map__resolution']), m['Shanghai_map__shape']
+    x1, y1 = o[0] + w * res, o[1] + h * res
+    extra = [[o[0] + 0.013, o[1] + 0.021, 0.7], [x1 - 0.011, y1 - 0.017, -2.4], [o[0] + 0.5 * w * res, y1 - 1e-3, 1.6],
+             [x1 + 3.0, o[1] + 0.5 * h * res, 3.0], [o[0] - 1e-9, o[1] + 10.0, 0.0], [-500.0, 0.0, 1.0]]
+    return np.concatenate([poses, np.array(extra)])
+
+
+def make_large_map_golden():
+    """BASELINE config C4 'large maps': the reference's own ScanSimulator2D on (a) assets/maps/levine (2048 x 2048),
+    (b) the Shanghai image upsampled x2 (4000 x 4000) and x4 (8000 x 8000) by pixel replication with the resolution
+    divided accordingly, (c) the x2 map under an origin with a yaw.  Noise-free scans (laser_models.py:429-454 with
+    rng None) -> tests/golden/scans_large.npz; the levine occupancy -> tests/golden/maps_large.npz.  The upsampled
+    occupancies are rebuilt by the tests from the Shanghai bits (np.kron), exactly as written to disk here."""
+    from PIL import Image
+    from f110_gym.envs.laser_models import ScanSimulator2D
+    out = {}
+    # ---- (a) levine, as it lies in the reference tree
+    lev_dir = os.path.join(REF_ROOT, 'assets', 'maps') + '/'
+    packed = pack_map(lev_dir, 'levine')
+    np.savez_compressed(os.path.join(HERE, 'maps_large.npz'), **packed)
+    sim = ScanSimulator2D(1080, 4.7)
+    sim.set_map(lev_dir + 'levine.yaml', '.png')
+    free = np.argwhere(sim.dt > 0.3)
+    rng = np.random.default_rng(11)
+    pick = free[rng.choice(len(free), 72, replace=False)]
+    o = packed['levine__origin']; res = float(packed['levine__resolution'])
+    poses = np.column_stack([o[0] + (pick[:, 1] + rng.uniform(0, 1, 72)) * res, o[1] + (pick[:, 0] + rng.uniform(0, 1, 72)) * res,
+                             rng.uniform(-np.pi, np.pi, 72)])
+    poses = np.concatenate([poses, [[o[0] + 1e-3, o[1] + 1e-3, 0.8], [o[0] + 2048 * res - 1e-3, o[1] + 2048 * res - 1e-3, -2.3],
+                                    [o[0] - 5.0, o[1] + 20.0, 0.0], [300.0, 300.0, 1.0]]])
+    out['levine__poses'] = poses
+    out['levine__scans'] = np.stack([sim.scan(p, None) for p in poses])
+    out['levine__dt_probe'] = np.array([sim.dt[-1, -1], sim.dt[0, 0], sim.dt.max(), sim.dt.sum()])
+    print('levine', out['levine__scans'].shape, 'range', out['levine__scans'].min(), out['levine__scans'].max())
+    # ---- (b), (c) upsampled Shanghai
+    m = dict(np.load(os.path.join(HERE, 'maps.npz')))
+    shape = tuple(int(v) for v in m['Shanghai_map__shape'])
+    free = np.unpackbits(m['Shanghai_map__bits'])[:shape[0] * shape[1]].reshape(shape).astype(bool)
+    o, res = m['Shanghai_map__origin'], float(m['Shanghai_map__resolution'])
+    for k, theta in ((2, 0.0), (4, 0.0), (2, 0.3)):
+        big = np.kron(free, np.ones((k, k), bool))
+        name = 'Shanghai_x%d%s' % (k, '_rot' if theta else '')
+        Image.fromarray(np.where(big, 254, 0).astype(np.uint8)[::-1], mode='L').save(TMP + name + '.png')
+        origin = [float(o[0]), float(o[1]), 0.0] if not theta else [3.5, -7.25, theta]
+        with open(TMP + name + '.yaml', 'w') as f:
+            f.write("image: %s.png\nresolution: %r\norigin: [%r, %r, %r]\nnegate: 0\noccupied_thresh: 0.45\nfree_thresh: 0.196\n"
+                    % (name, res / k, origin[0], origin[1], origin[2]))
+        sim = ScanSimulator2D(1080, 4.7)
+        sim.set_map(TMP + name + '.yaml', '.png')
+        assert sim.dt.shape == (shape[0] * k, shape[1] * k)
+        poses = large_map_poses('Shanghai', k)
+        if theta:
+            mx, my = poses[:, 0] - o[0], poses[:, 1] - o[1]
+            c, s_ = np.cos(theta), np.sin(theta)
+            poses = np.stack([origin[0] + c * mx - s_ * my, origin[1] + s_ * mx + c * my, poses[:, 2] + theta], axis=1)
+        out[name + '__origin'] = np.array(origin)
+        out[name + '__resolution'] = np.float64(res / k)
+        out[name + '__poses'] = poses
+        out[name + '__scans'] = np.stack([sim.scan(p, None) for p in poses])
+        out[name + '__dt_probe'] = np.array([sim.dt[-1, -1], sim.dt[0, 0], sim.dt.max(), sim.dt.sum()])
+        print(name, sim.dt.shape, out[name + '__scans'].shape, 'range', out[name + '__scans'].min(), out[name + '__scans'].max())
+        del sim, big
+    np.savez_compressed(os.path.join(HERE, 'scans_large.npz'), **out)
+    for f in ('maps_large.npz', 'scans_large.npz'):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'reward':
+    if len(sys.argv) > 1 and sys.argv[1] == 'large':
+        make_large_map_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'c1':
+        make_c1_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'reward':
         make_reward_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == 'gap_follow':
         make_gap_follow_golden()     # only the consumer-side fixture
@@ -293,3 +380,4 @@ if __name__ == '__main__':
         make_gap_follow_golden()
         make_reward_golden()
         make_rotated_scan_golden()
+        make_large_map_golden()

@@ -26,6 +26,34 @@ def golden_map(name):
     return res * distance_transform_edt(img), res, [float(v) for v in m[name + '__origin']]
 
 
+LARGE_MAPS = ('levine', 'Shanghai_x2', 'Shanghai_x4', 'Shanghai_x2_rot')
+
+
+@functools.lru_cache(maxsize=2)
+def large_map(name):
+    """BASELINE config C4 'large maps' -> (dt fp64 [H,W], resolution, origin[3], poses, reference scans).
+    levine (2048 x 2048) comes packed in maps_large.npz; Shanghai_x2 / _x4 / _x2_rot are rebuilt from the Shanghai bits by
+    pixel replication (np.kron), exactly what make_golden.py wrote to disk for the reference (resolution / k)."""
+    from scipy.ndimage import distance_transform_edt
+    g = load('scans_large')
+    if name == 'levine':
+        m = load('maps_large')
+        shape = tuple(int(v) for v in m['levine__shape'])
+        free = np.unpackbits(m['levine__bits'])[:shape[0] * shape[1]].reshape(shape).astype(bool)
+        res, origin = float(m['levine__resolution']), [float(v) for v in m['levine__origin']]
+    else:
+        m = load('maps')
+        shape = tuple(int(v) for v in m['Shanghai_map__shape'])
+        free = np.unpackbits(m['Shanghai_map__bits'])[:shape[0] * shape[1]].reshape(shape).astype(bool)
+        k = int(name.split('_x')[1][0])
+        free = np.kron(free, np.ones((k, k), bool))
+        res, origin = float(g[name + '__resolution']), [float(v) for v in g[name + '__origin']]
+    dt = res * distance_transform_edt(np.where(free, 255., 0.))
+    probe = g[name + '__dt_probe']
+    assert dt[-1, -1] == probe[0] and dt[0, 0] == probe[1] and dt.max() == probe[2], "EDT differs from the reference's"
+    return dt, res, origin, g[name + '__poses'], g[name + '__scans']
+
+
 def write_map_files(name, directory):
     """Materialise a golden map as <directory>/<name>.yaml + .png (the reference's on-disk format)."""
     from PIL import Image

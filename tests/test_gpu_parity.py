@@ -161,6 +161,39 @@ def test_rotated_origin_scans_golden():
     sim.close()
 
 
+@pytest.mark.parametrize("name", H.LARGE_MAPS)
+def test_large_map_scans_golden_and_oracle(name):
+    """BASELINE config C4 'large maps': levine 2048^2, Shanghai x2 (4000^2, 128 MB), x4 (8000^2, 512 MB: not L2-resident)
+    and x2 under a rotated origin.  The guarded fixed-point cell index keeps 20 / 20 / 19 fraction bits on these maps
+    instead of the 21 of the 2000^2 map.  Noise-free scans against the reference's own (tests/golden/scans_large.npz)
+    and against the oracle: bit-exact on the axis-aligned origins, <= 1e-6 m on >= 99.9 % of beams on the rotated one;
+    poses on the track, next to the map border, on it and outside."""
+    from oracle.f110_oracle import Oracle
+    _torch()
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim
+    dt, res, origin, poses, ref = H.large_map(name)
+    n = len(poses)
+    s, c, _, _, _ = H.tables()
+    orc = Oracle(1, 1); orc.set_tables(s, c); orc.set_map_arrays(dt, res, origin)
+    want = np.stack([orc.scan(p)[0] for p in poses])
+    sim = BatchSim(n, 1, outputs=ALL_OUTPUTS, noise_std=0.0)
+    sim.set_tables(s, c)
+    sim.set_map_arrays(dt, res, origin)
+    sim.sim_reset(poses[:, None, :])
+    o = sim.step(None, np.zeros((n, 1, 1080)))
+    torch.cuda.synchronize()
+    got = o['scans_f64'].cpu().numpy()[:, 0]
+    sim.close()
+    d_ref, d_orc = np.abs(got - ref), np.abs(got - want)
+    print(name, dt.shape, 'vs reference max', d_ref.max(), 'exact', float((d_ref == 0).mean()), '| vs oracle max', d_orc.max())
+    assert (d_ref <= SCAN_TOL).mean() >= SCAN_FRAC
+    assert d_orc.max() == 0.0 or name.endswith('_rot')
+    assert (d_orc <= SCAN_TOL).mean() >= SCAN_FRAC
+    if not name.endswith('_rot'):
+        assert d_ref.max() == 0.0
+
+
 def test_c1_single_agent_sim_rollout():
     g = H.load('rollout_c1_single')
     be = make_gpu(1, 'Shanghai_map')

@@ -195,3 +195,21 @@ def test_shaped_reward_oracle_matches_reference():
         got = np.array([o(g['obs'][k], np.array([g['episode_start'][k]], np.uint8))[0] for k in range(len(g[key]))])
         assert np.abs(got - g[key]).max() < 1e-12
         assert (got == -50.0).any() and (np.abs(got) < 5).any()
+
+
+@pytest.mark.parametrize("name", H.LARGE_MAPS)
+def test_large_map_scans_golden(name):
+    """BASELINE config C4 'large maps' (levine 2048^2, Shanghai x2 = 4000^2, x4 = 8000^2, x2 under a rotated origin):
+    the oracle's noise-free scans against the reference's own (laser_models.py:55-186), poses on the track, at the map
+    border and outside it.  Axis-aligned origins are bit-exact; the rotated one within 1e-6 m on >= 99.9 % of beams."""
+    dt, res, origin, poses, ref = H.large_map(name)
+    o = Oracle(1, 1)
+    s, c, _, _, _ = H.tables()
+    o.set_tables(s, c)
+    o.set_map_arrays(dt, res, origin)
+    got = np.stack([o.scan(p)[0] for p in poses])
+    d = np.abs(got - ref)
+    print(name, dt.shape, 'max', d.max(), 'exact fraction', float((d == 0).mean()))
+    assert (d <= 1e-6).mean() >= 0.999
+    if not name.endswith('_rot'):
+        assert d.max() == 0.0
