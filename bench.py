@@ -332,6 +332,7 @@ def main():
             cenv.step(acts[k])
         looks, rays = cenv.backend.lookup_count()
         max_lookups = cenv.backend.max_lookups
+        redone_rays = cenv.backend.redone_rays
         cenv.close()
         lbar = looks / max(rays, 1)
         bytes_per_ray = 8.0 * lbar + 8.0                      # L-bar fp64 cells + fp64 range out
@@ -346,6 +347,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
                     "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar, "longest_ray_lookups": max_lookups,
+                    "rays_redone_exactly": redone_rays, "rays_counted": rays,
                     "bytes_per_ray": bytes_per_ray,
                     "sector_level": {"bytes_per_ray": 32.0 * lbar + 8.0, "gbs": (32.0 * lbar + 8.0) * E * A * B / (lidar_ms * 1e-3) / 1e9,
                                      "note": "32-byte sector per gather instead of the 8 useful bytes (SURVEY 8d)"},

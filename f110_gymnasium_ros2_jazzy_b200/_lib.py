@@ -25,7 +25,7 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_map_image", "f110_get_map", "f110_set_tables",
            "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_sim_reset_host", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
-           "f110_kernel_launches", "f110_max_lookups", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_reward_create", "f110_reward_destroy",
+           "f110_kernel_launches", "f110_max_lookups", "f110_redone_rays", "f110_map_generation", "f110_debug_unit_timeline", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_reward_create", "f110_reward_destroy",
            "f110_reward_compute"]
 
 
@@ -103,6 +103,12 @@ def load():
     L.f110_reward_compute.argtypes = [vp, vp, vp, vp, vp, vp]
     L.f110_max_lookups.argtypes = [vp]
     L.f110_max_lookups.restype = C.c_int64
+    L.f110_redone_rays.argtypes = [vp]
+    L.f110_redone_rays.restype = C.c_int64
+    L.f110_debug_unit_timeline.argtypes = [vp, vp, C.c_int64]
+    L.f110_debug_unit_timeline.restype = C.c_int64
+    L.f110_map_generation.argtypes = [vp]
+    L.f110_map_generation.restype = C.c_int64
     L.f110_kernel_launches.argtypes = [vp]
     L.f110_kernel_launches.restype = C.c_int64
     if L.f110_abi_version() != F110_ABI_VERSION:

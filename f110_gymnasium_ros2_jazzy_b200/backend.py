@@ -317,6 +317,7 @@ class BatchSim(object):
         a, b = C.c_uint64(0), C.c_uint64(0)
         _lib.check(self.lib.f110_get_lookup_count(self.h, C.byref(a), C.byref(b)))
         self.max_lookups = int(self.lib.f110_max_lookups(self.h))
+        self.redone_rays = int(self.lib.f110_redone_rays(self.h))
         return a.value, b.value
 
     @property

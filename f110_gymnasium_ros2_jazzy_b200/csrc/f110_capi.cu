@@ -59,6 +59,7 @@ struct F110Sim {
     StepScratch sc;
     MapView map;
     bool map_set = false;
+    int64_t map_generation = 0;   // bumped by every set_map: a CUDA graph captured before holds the old map by value
     bool count_lookups = false;
     bool narrow_fraction = false;
     bool debug_sync = false;
@@ -67,13 +68,16 @@ struct F110Sim {
     char* scratch_blob = nullptr; size_t scratch_bytes = 0;
     double* d_tables = nullptr;   // params[A][18], sim_params[18], sines, cosines, scan_angles, beam_cos, side_dist
     double* d_map = nullptr;
+    double2* d_lidar_tables = nullptr;   // beam_tt[B], dir_fx[theta_dis]
+    std::vector<double> h_sines, h_cosines;   // host copies: dir_fx is rebuilt from them whenever the map changes
     // host-buffer path (f110_step_host)
     cudaStream_t host_stream = nullptr;
     char* io_blob = nullptr; size_t io_bytes = 0;
     int64_t launches = 0;
     bool timing = false;
     unsigned long long max_lookups = 0;   // longest ray (lookups) seen, refreshed by f110_get_lookup_count
-    int lidar_threads = 128;
+    unsigned long long redone_rays = 0;   // rays the lidar kernel redid in exact arithmetic, refreshed likewise
+    int lidar_blocks = 0;         // CTAs of one resident wave of the lidar kernel (persistent warps)
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
 };
 
@@ -91,18 +95,22 @@ void layout_state(Arena& a, SimState& st, int N, int NA) {
     st.near_start = a.take<uint8_t>(NA); st.collisions = a.take<uint8_t>(NA);
 }
 
-void layout_scratch(Arena& a, StepScratch& sc, int NA, int B) {
+void layout_scratch(Arena& a, StepScratch& sc, int NA, int B, bool timeline) {
     sc.scan_x = a.take<double>(NA); sc.scan_y = a.take<double>(NA); sc.pre_yaw = a.take<double>(NA);
-    sc.theta0 = a.take<double>(NA);
+    sc.head = a.take<double>((size_t)NA * 4);
     sc.ttc_hit = a.take<int32_t>(NA);
     sc.lookups = a.take<unsigned long long>(4);
     sc.stats = a.take<double>(F110_NUM_STATS);
     sc.scan = a.take<double>((size_t)NA * B);
-    sc.num_units = (unsigned)((((size_t)NA * B + 31) / 32 + 3) / 4 * 4);
-    sc.front_units = ((sc.num_units / 8 + 3) / 4) * 4 + 4;
-    sc.heavy_cnt = a.take<unsigned>(2);
-    sc.heavy_list = a.take<unsigned>(2 * (size_t)sc.front_units);
-    sc.unit_heavy = a.take<uint8_t>(2 * (size_t)sc.num_units);
+    sc.num_units = (unsigned)((size_t)NA * ((B + 31) / 32));
+    // capacities of the three heavy-unit lists (classes >= 96 / 48 / 24 lookups); a list that overflows sends the rest of
+    // its class to the light region, which costs order, never correctness
+    sc.cap[0] = sc.num_units / 16 + 8; sc.cap[1] = sc.num_units / 8 + 8; sc.cap[2] = sc.num_units / 4 + 8;
+    sc.ctrl = a.take<unsigned>(F110_CTRL_WORDS);
+    const size_t ncap = (size_t)sc.cap[0] + sc.cap[1] + sc.cap[2];
+    sc.list[0] = a.take<unsigned>(ncap); sc.list[1] = a.take<unsigned>(ncap);
+    sc.cls[0] = a.take<unsigned>(sc.num_units); sc.cls[1] = a.take<unsigned>(sc.num_units);
+    sc.timeline = (timeline && sc.num_units <= (1u << 22)) ? a.take<uint4>(sc.num_units) : nullptr;
 }
 
 FastDiv make_fast_div(uint32_t d) {
@@ -145,13 +153,13 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
         const cudaError_t de = cudaStreamSynchronize(s);                                                           \
         if (de != cudaSuccess) return fail(F110_ERR_CUDA, "%s: %s", name, cudaGetErrorString(de));                 \
     }
-    launch_dynamics(sim->c, sim->st, sim->sc, io, s);
+    CUDA_TRY(launch_dynamics(sim->c, sim->map, sim->st, sim->sc, io, s));
     DEBUG_SYNC("dynamics_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[1], s));
-    launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_threads, s);
+    CUDA_TRY(launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_blocks, s));
     DEBUG_SYNC("lidar_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
-    launch_post(sim->c, sim->st, sim->sc, io, s);
+    CUDA_TRY(launch_post(sim->c, sim->st, sim->sc, io, s));
     DEBUG_SYNC("post_kernel")
 #undef DEBUG_SYNC
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[3], s));
@@ -193,16 +201,19 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
     sim->narrow_fraction = (cfg->flags & F110_FLAG_NARROW_FRACTION) != 0;
     sim->debug_sync = getenv("F110_DEBUG_SYNC") != nullptr;
-    if (const char* e = getenv("F110_LIDAR_THREADS")) {   // tuning knob, multiple of 32 in [32, 256]
-        const int t = atoi(e);
-        if (t >= 32 && t <= 128 && t % 32 == 0) sim->lidar_threads = t;
+    sim->lidar_blocks = lidar_resident_blocks(A == 1);
+    sim->sc.ordered = 0;   // set below, once the unit count is known
+    if (sim->lidar_blocks < 1) {
+        cudaGetLastError();
+        delete sim;
+        return fail(F110_ERR_CUDA, "cannot query the lidar kernel's occupancy (is this an sm_100a device?)");
     }
 
     Arena measure;
     layout_state(measure, sim->st, N, NA);
     sim->state_bytes = (measure.used + 255) & ~size_t(255);
     Arena measure2;
-    layout_scratch(measure2, sim->sc, NA, B);
+    layout_scratch(measure2, sim->sc, NA, B, sim->count_lookups);
     sim->scratch_bytes = (measure2.used + 255) & ~size_t(255);
     const size_t ntab = (size_t)A * F110_NUM_PARAMS + F110_NUM_PARAMS + 2 * (size_t)cfg->theta_dis + 3 * (size_t)B;
 
@@ -212,6 +223,8 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     if (e == cudaSuccess) e = cudaMemset(sim->state_blob, 0, sim->state_bytes);
     if (e == cudaSuccess) e = cudaMemset(sim->scratch_blob, 0, sim->scratch_bytes);
     if (e == cudaSuccess) e = cudaMemset(sim->d_tables, 0, ntab * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&sim->d_lidar_tables, ((size_t)B + cfg->theta_dis) * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMemset(sim->d_lidar_tables, 0, ((size_t)B + cfg->theta_dis) * sizeof(double2));
     if (e == cudaSuccess) {
         // host_stream_rank r > 0: the r-th highest stream priority the device offers, so that a caller pipelining several
         // handles (f110_step_host_multi) gets handle 1's kernels finished -- and its download started -- first
@@ -227,7 +240,19 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
         return F110_ERR_CUDA;
     }
     Arena a; a.base = sim->state_blob; layout_state(a, sim->st, N, NA);
-    Arena b; b.base = sim->scratch_blob; layout_scratch(b, sim->sc, NA, B);
+    Arena b; b.base = sim->scratch_blob; layout_scratch(b, sim->sc, NA, B, sim->count_lookups);
+    sim->sc.ordered = (size_t)sim->sc.num_units <= (size_t)48 * 4 * (size_t)(sim->lidar_blocks > 0 ? sim->lidar_blocks : 1) ? 1u : 0u;
+    // before the first step no unit is on a list: every unit is class 3 (light, natural order)
+    {
+        const std::vector<unsigned> light(sim->sc.num_units, 3u);
+        e = cudaMemcpy(sim->sc.cls[0], light.data(), light.size() * sizeof(unsigned), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(sim->sc.cls[1], light.data(), light.size() * sizeof(unsigned), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        fail(F110_ERR_CUDA, "scratch initialisation failed: %s", cudaGetErrorString(e));
+        f110_destroy(sim);
+        return F110_ERR_CUDA;
+    }
 
     double* t = sim->d_tables;
     SimConst& c = sim->c;
@@ -238,6 +263,10 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     c.lidar_max = (float)cfg->lidar_max; c.seed = cfg->seed;
     c.noise_key = (uint32_t)cfg->seed ^ ((uint32_t)(cfg->seed >> 32) * 0x85EBCA6Bu) ^ 0x46313130u;
     c.div_B = make_fast_div((uint32_t)B); c.div_A = make_fast_div((uint32_t)A);
+    c.ups = (unsigned)((B + 31) / 32); c.div_ups = make_fast_div(c.ups);
+    for (int r = 0; r < 10; ++r) c.philox_key[r] = c.noise_key + (uint32_t)r * 0x9E3779B9u;
+    c.obs_rcp = 1.0f / c.lidar_max;
+    c.obs_fast_div = c.lidar_max == 30.0f ? 1 : 0;
     // ScanSimulator2D.__init__ laser_models.py:367-368
     const double angle_increment = cfg->fov / (B - 1);
     c.theta_inc = cfg->theta_dis * angle_increment / (2. * F110_PI);
@@ -248,6 +277,9 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     c.scan_angles = t; t += B;
     c.beam_cos = t; t += B;
     c.side_dist = t; t += B;
+    c.beam_tt = sim->d_lidar_tables;
+    c.dir_fx = sim->d_lidar_tables + B;
+    sim->h_sines.assign(cfg->theta_dis, 0.0); sim->h_cosines.assign(cfg->theta_dis, 1.0);
 
     std::vector<double> hp((size_t)(A + 1) * F110_NUM_PARAMS);
     for (int i = 0; i <= A; ++i) memcpy(&hp[(size_t)i * F110_NUM_PARAMS], params, sizeof(double) * F110_NUM_PARAMS);
@@ -268,22 +300,66 @@ void f110_destroy(F110Sim* sim) {
     if (!sim) return;
     Guard g(sim->cfg.device);
     if (sim->host_stream) { cudaStreamSynchronize(sim->host_stream); cudaStreamDestroy(sim->host_stream); }
-    cudaFree(sim->state_blob); cudaFree(sim->scratch_blob); cudaFree(sim->d_tables); cudaFree(sim->d_map);
+    cudaFree(sim->state_blob); cudaFree(sim->scratch_blob); cudaFree(sim->d_tables); cudaFree(sim->d_map); cudaFree(sim->d_lidar_tables);
     cudaFree(sim->io_blob);
     for (cudaEvent_t e : sim->tev) cudaEventDestroy(e);
     delete sim;
 }
 
-// fixed-point format of the guarded fast cell index (dt_lookup): as many fraction bits as a 32-bit quotient leaves
-static void set_fixed_point(MapView& m, int width, int height, bool narrow) {
-    const unsigned big = (unsigned)(width > height ? width : height);
-    unsigned bits = 0;
-    while ((big >> bits) != 0u) ++bits;            // bit_length(max(W, H)) <= 16
-    m.fx_bits = 32u - bits > 24u ? 24u : 32u - bits;
-    if (narrow) m.fx_bits = 6u;                    // F110_FLAG_NARROW_FRACTION
-    m.fx_mask = (1u << m.fx_bits) - 1u;
-    m.inv_fx = (1.0 / m.res) * (double)(1u << m.fx_bits);
-    m.w_fx = (unsigned)width << m.fx_bits; m.h_fx = (unsigned)height << m.fx_bits;
+// The lidar kernel's direction table: table direction k rotated into the map frame and scaled to fixed-point cells per
+// metre.  Depends on the sin / cos tables and on the map (origin yaw, resolution, fraction bits): rebuilt by both setters.
+static int refresh_direction_table(F110Sim* sim) {
+    if (!sim->map_set) return F110_OK;
+    const MapView& m = sim->map;
+    const size_t n = sim->h_sines.size();
+    std::vector<double2> dir(n);
+    for (size_t k = 0; k < n; ++k) {
+        const double cs = sim->h_cosines[k], sn = sim->h_sines[k];
+        dir[k].x = (cs * m.oc + sn * m.os) * m.inv_fx;
+        dir[k].y = (-cs * m.os + sn * m.oc) * m.inv_fx;
+    }
+    CUDA_TRY(cudaMemcpy(const_cast<double2*>(sim->c.dir_fx), dir.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+    return F110_OK;
+}
+
+// Installs a DENSE device map [H][W] as the handle's padded map (see MapView) and frees `dense`.
+static int install_map(F110Sim* sim, double* dense, int height, int width, double resolution,
+                       double orig_x, double orig_y, double orig_cos, double orig_sin) {
+    // fixed-point format of the lidar kernel's fast march: as many fraction bits as a 32-bit coordinate leaves beside the
+    // cell index of the larger side (+ 1: the map is stored one cell in from the padded array's corner)
+    auto bit_length = [](unsigned v) { unsigned b = 0; while ((v >> b) != 0u) ++b; return b; };
+    MapView m;
+    memset(&m, 0, sizeof(m));
+    const unsigned side = (unsigned)(width > height ? width : height) + 1u;
+    m.fx_bits = 32u - bit_length(side) > 24u ? 24u : 32u - bit_length(side);
+    m.guard = sim->narrow_fraction ? (1u << (m.fx_bits - 5u)) : 2u;     // F110_FLAG_NARROW_FRACTION: 1/16 of every cell undecided
+    m.guard_mask = ((1u << m.fx_bits) - 1u) & ~(2u * m.guard - 1u);
+    const size_t prows = (size_t)1 << (32u - m.fx_bits);
+    const size_t pitch = prows + 16;
+    if ((double)prows * (double)pitch >= 2147483648.0) { cudaFree(dense); return fail(F110_ERR_INVALID, "map too large once padded (%zu x %zu cells)", prows, pitch); }
+    if (map_min_positive(dense, (size_t)height * width, &m.min_positive, sim->host_stream) != cudaSuccess) {
+        cudaFree(dense); cudaGetLastError();
+        return fail(F110_ERR_CUDA, "map scan failed");
+    }
+    double* padded = nullptr;
+    cudaError_t e = cudaMalloc(&padded, prows * pitch * sizeof(double));
+    if (e == cudaSuccess) e = launch_pad_map(dense, height, width, padded, (int)prows, (int)pitch, sim->host_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sim->host_stream);
+    cudaFree(dense);
+    if (e != cudaSuccess) { cudaFree(padded); cudaGetLastError(); return fail(F110_ERR_CUDA, "map padding: %s", cudaGetErrorString(e)); }
+    cudaFree(sim->d_map);
+    sim->d_map = padded;
+    m.dt = padded; m.H = height; m.W = width; m.pitch = (int)pitch; m.prows = (int)prows;
+    m.last = (height - 1) * width + (width - 1);
+    m.res = resolution;
+    m.inv_fx = (1.0 / resolution) * (double)(1u << m.fx_bits);
+    m.fx_off = (double)(1u << m.fx_bits) - (double)m.guard;
+    m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
+    m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
+    sim->map = m;
+    sim->map_set = true;
+    sim->map_generation += 1;
+    return refresh_direction_table(sim);
 }
 
 int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, double resolution,
@@ -298,15 +374,7 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
     CUDA_TRY(cudaMalloc(&d, bytes));
     cudaError_t e = cudaMemcpy(d, dt, bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return fail(F110_ERR_CUDA, "map upload: %s", cudaGetErrorString(e)); }
-    cudaFree(sim->d_map);
-    sim->d_map = d;
-    MapView& m = sim->map;
-    m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; set_fixed_point(m, width, height, sim->narrow_fraction);
-    m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
-    m.wres = width * resolution; m.hres = height * resolution;   // laser_models.py:79
-    sim->map_set = true;
-    return F110_OK;
+    return install_map(sim, d, height, width, resolution, orig_x, orig_y, orig_cos, orig_sin);
 }
 
 int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, int32_t width, double resolution,
@@ -326,15 +394,7 @@ int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, i
     if (e == cudaSuccess) rc = edt_device(d_mask, height, width, resolution, d, sim->host_stream);
     cudaFree(d_mask);
     if (e != cudaSuccess || rc != 0) { cudaFree(d); cudaGetLastError(); return fail(F110_ERR_CUDA, "device EDT failed"); }
-    cudaFree(sim->d_map);
-    sim->d_map = d;
-    MapView& m = sim->map;
-    m.dt = d; m.H = height; m.W = width; m.last = (height - 1) * width + (width - 1);
-    m.res = resolution; set_fixed_point(m, width, height, sim->narrow_fraction);
-    m.ox = orig_x; m.oy = orig_y; m.oc = orig_cos; m.os = orig_sin;
-    m.wres = width * resolution; m.hres = height * resolution;
-    sim->map_set = true;
-    return F110_OK;
+    return install_map(sim, d, height, width, resolution, orig_x, orig_y, orig_cos, orig_sin);
 }
 
 int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells) {
@@ -344,7 +404,9 @@ int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells) {
     if ((size_t)capacity_cells < cells) return fail(F110_ERR_INVALID, "buffer too small for %d x %d cells", sim->map.H, sim->map.W);
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(dt_host, sim->d_map, cells * sizeof(double), cudaMemcpyDeviceToHost));
+    (void)cells;
+    CUDA_TRY(cudaMemcpy2D(dt_host, (size_t)sim->map.W * sizeof(double), sim->d_map + sim->map.pitch + 1, (size_t)sim->map.pitch * sizeof(double),
+                          (size_t)sim->map.W * sizeof(double), (size_t)sim->map.H, cudaMemcpyDeviceToHost));
     return F110_OK;
 }
 
@@ -355,7 +417,9 @@ int f110_set_tables(F110Sim* sim, const double* sines, const double* cosines) {
     const size_t n = sizeof(double) * sim->cfg.theta_dis;
     CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.sines), sines, n, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.cosines), cosines, n, cudaMemcpyHostToDevice));
-    return F110_OK;
+    sim->h_sines.assign(sines, sines + sim->cfg.theta_dis);
+    sim->h_cosines.assign(cosines, cosines + sim->cfg.theta_dis);
+    return refresh_direction_table(sim);
 }
 
 int f110_set_beam_tables(F110Sim* sim, const double* scan_angles, const double* beam_cosines, const double* side_distances) {
@@ -368,6 +432,9 @@ int f110_set_beam_tables(F110Sim* sim, const double* scan_angles, const double* 
     CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.scan_angles), scan_angles, n, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.beam_cos), beam_cosines, n, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(const_cast<double*>(sim->c.side_dist), side_distances, n, cudaMemcpyHostToDevice));
+    std::vector<double2> bt(sim->cfg.num_beams);
+    for (int i = 0; i < sim->cfg.num_beams; ++i) { bt[i].x = beam_cosines[i]; bt[i].y = side_distances[i]; }
+    CUDA_TRY(cudaMemcpy(const_cast<double2*>(sim->c.beam_tt), bt.data(), bt.size() * sizeof(double2), cudaMemcpyHostToDevice));
     return F110_OK;
 }
 
@@ -387,9 +454,8 @@ int f110_sim_reset(F110Sim* sim, const double* poses, int32_t num_poses, const u
     if (!sim || !poses) return fail(F110_ERR_INVALID, "null argument");
     if (num_poses != sim->cfg.num_agents) return fail(F110_ERR_POSE_COUNT, "Number of poses for reset does not match number of agents.");
     Guard g(sim->cfg.device);
-    launch_sim_reset(sim->c, sim->st, poses, env_mask, (cudaStream_t)stream);
+    CUDA_TRY(launch_sim_reset(sim->c, sim->st, poses, env_mask, (cudaStream_t)stream));
     sim->launches += 1;
-    CUDA_TRY(cudaPeekAtLastError());
     return F110_OK;
 }
 
@@ -405,9 +471,9 @@ int f110_sim_reset_host(F110Sim* sim, const double* poses, int32_t num_poses, co
     cudaError_t e = cudaMemcpyAsync(d_poses, poses, NA * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && env_mask) e = cudaMemcpyAsync(d_mask, env_mask, N, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
-        launch_sim_reset(sim->c, sim->st, d_poses, d_mask, s);
+        e = launch_sim_reset(sim->c, sim->st, d_poses, d_mask, s);
         sim->launches += 1;
-        e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
     cudaFree(d_poses);
     if (e != cudaSuccess) return fail(F110_ERR_CUDA, "f110_sim_reset_host: %s", cudaGetErrorString(e));
@@ -550,11 +616,22 @@ int f110_get_lookup_count(F110Sim* sim, uint64_t* lookups, uint64_t* rays) {
     if (!sim->count_lookups) return fail(F110_ERR_INVALID, "handle was created without F110_FLAG_COUNT_LOOKUPS");
     Guard g(sim->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
-    unsigned long long h[3];
+    unsigned long long h[4];
     CUDA_TRY(cudaMemcpy(h, sim->sc.lookups, sizeof(h), cudaMemcpyDeviceToHost));
     *lookups = h[0]; *rays = h[1];
     sim->max_lookups = h[2];
+    sim->redone_rays = h[3];
     return F110_OK;
+}
+
+int64_t f110_debug_unit_timeline(F110Sim* sim, uint32_t* out, int64_t capacity_units) {
+    if (!sim) return 0;
+    if (!out) return sim->sc.timeline ? (int64_t)sim->sc.num_units : 0;
+    if (!sim->sc.timeline || capacity_units < (int64_t)sim->sc.num_units) return fail(F110_ERR_INVALID, "no timeline (F110_FLAG_COUNT_LOOKUPS) or buffer too small");
+    Guard g(sim->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, sim->sc.timeline, (size_t)sim->sc.num_units * 16, cudaMemcpyDeviceToHost));
+    return (int64_t)sim->sc.num_units;
 }
 
 int f110_set_kernel_timing(F110Sim* sim, int32_t enable) {
@@ -582,6 +659,8 @@ int f110_get_kernel_timing(F110Sim* sim, double* ms3, int64_t* steps) {
 }
 
 int64_t f110_max_lookups(const F110Sim* sim) { return sim ? (int64_t)sim->max_lookups : 0; }
+int64_t f110_redone_rays(const F110Sim* sim) { return sim ? (int64_t)sim->redone_rays : 0; }
+int64_t f110_map_generation(const F110Sim* sim) { return sim ? sim->map_generation : 0; }
 
 int64_t f110_kernel_launches(const F110Sim* sim) { return sim ? sim->launches : 0; }
 

@@ -16,6 +16,7 @@
 #include "f110_kernels.cuh"
 
 #include <math.h>
+#include <string.h>
 
 namespace {
 
@@ -141,27 +142,12 @@ __device__ __forceinline__ void pid(double speed, double steer, double cur_speed
 
 // ---------------------------------------------------------------- K1: dynamics
 
-__global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+__global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
     cudaGridDependencySynchronize();   // PDL: the previous step's post kernel (or whatever precedes in the stream) is done
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     // Every global load this thread needs is issued before the first store or branch that depends on one: the kernel is a
     // single dependent chain per thread, and with a cold L2 each load left in program order behind a branch costs a DRAM
-    // round trip of its own (the publish copy, the masks, the state, the action and the parameters were five in a row).
-    //
-    // (1) The launch-order history the lidar kernel recorded during the previous step (the "next" halves of the
-    // buffers; its length was latched into heavy_cnt[0] by the post kernel) becomes this step's order.  A copy rather
-    // than a pointer flip, so a captured CUDA graph stays valid step after step.
-    const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned nw = sc.num_units / 4;                        // num_units is padded to a multiple of 4
-    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(sc.unit_heavy + sc.num_units);
-    uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sc.unit_heavy);
-    uint32_t v0[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const unsigned k = (unsigned)s + j * stride; v0[j] = k < nw ? src[k] : 0u; }
-    const unsigned n_heavy = sc.heavy_cnt[0];
-    const unsigned heavy0 = (unsigned)s < sc.front_units ? sc.heavy_list[sc.front_units + s] : 0u;   // used only if s < n_heavy
-
-    // (2) this thread's vehicle
+    // round trip of its own (the masks, the state, the action and the parameters were four in a row).
     const bool veh = s < c.NA;
     const int env = veh ? s / c.A : 0;
     const int a = s - env * c.A;
@@ -192,22 +178,9 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
     }
     const VehParams p = load_params(c.params + (veh ? a : 0) * F110_NUM_PARAMS);
 
-    // (1, continued) the stores of the copy
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const unsigned k = (unsigned)s + j * stride; if (k < nw) dst[k] = v0[j]; }
-    for (unsigned base = (unsigned)s + 8 * stride; base < nw; base += 8 * stride) {   // batches the grid does not cover at once
-        uint32_t v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; v[j] = k < nw ? src[k] : 0u; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const unsigned k = base + j * stride; if (k < nw) dst[k] = v[j]; }
-    }
-    if ((unsigned)s < n_heavy) sc.heavy_list[s] = heavy0;
-    for (unsigned k = (unsigned)s + stride; k < n_heavy; k += stride) sc.heavy_list[k] = sc.heavy_list[sc.front_units + k];
-
-    if (!veh || !active) return;
-    const bool rst = rst_flag != 0;
-
+    const bool run = veh && active;
+    const bool rst = run && rst_flag != 0;
+    if (run) {
     double x[7];
     if (rst) {
         // F110Env.reset bookkeeping (f110_env.py:440-451) + RaceCar.reset (base_classes.py:183-204)
@@ -300,8 +273,48 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, SimState st, 
     double ti = (double)c.theta_dis * (x[4] - c.fov / 2.) / (2. * F110_PI);
     ti = fmod(ti, (double)c.theta_dis);
     while (ti < 0) ti += (double)c.theta_dis;
-    sc.theta0[s] = ti;
+    // what the lidar kernel needs of this scan, in one 32-byte record: the start of the march in fixed-point map
+    // coordinates (xy_2_rc's translate / rotate, laser_models.py:66-77, then the scale 2^F / res), theta index of beam 0, speed
+    const double x_trans = sx - m.ox, y_trans = sy - m.oy;
+    double4 head;
+    head.x = (x_trans * m.oc + y_trans * m.os) * m.inv_fx + m.fx_off;
+    head.y = (-x_trans * m.os + y_trans * m.oc) * m.inv_fx + m.fx_off;
+    head.z = ti;
+    head.w = x[3];
+    reinterpret_cast<double4*>(sc.head)[s] = head;
     sc.ttc_hit[s] = 0;
+    }   // run
+
+    // The launch order the lidar kernel is about to use classes a scan's units by their rays of the PREVIOUS step; for a
+    // vehicle reset in this step those were taken from a pose that no longer exists.  A long unit met in the light region
+    // would extend the lidar kernel's tail by its whole length, so every unit of a reset scan that is not on a list already
+    // joins the third one (cost if it turns out short: none).  The warp does this together, lane k for units k, k + 32, ...
+    // of each reset scan in turn, with one atomic per 32 units; a list that is full leaves the rest where it is.  When most
+    // of the warp was reset (a global reset) the history is void anyway and nothing is done.
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned rst_mask = __ballot_sync(0xffffffffu, rst);
+    if (sc.ordered && rst_mask != 0u && __popc(rst_mask) <= 8) {
+        const unsigned par = sc.ctrl[CTRL_EPOCH] & 1u;
+        unsigned* cls = par ? sc.cls[1] : sc.cls[0];
+        unsigned* list2 = (par ? sc.list[1] : sc.list[0]) + sc.cap[0] + sc.cap[1];
+        while (rst_mask) {
+            const int j = __ffs(rst_mask) - 1;
+            rst_mask &= rst_mask - 1u;
+            const unsigned sj = (unsigned)__shfl_sync(0xffffffffu, s, j);
+            for (unsigned k0 = 0; k0 < c.ups; k0 += 32u) {
+                const unsigned k = k0 + lane;
+                const unsigned unit = sj * c.ups + k;
+                const bool light = k < c.ups && cls[unit] >= 3u;
+                const unsigned m_light = __ballot_sync(0xffffffffu, light);
+                if (m_light == 0u) continue;
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(sc.ctrl + CTRL_CUR + 2, (unsigned)__popc(m_light));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned slot = base + (unsigned)__popc(m_light & ((1u << lane) - 1u));
+                if (light && slot < sc.cap[2]) { list2[slot] = unit; cls[unit] = 2u; }   // the lidar kernel clamps the count to cap[2]
+            }
+        }
+    }
 }
 
 // Simulator.reset alone (base_classes.py:627-643): poses only, no step, env bookkeeping untouched
@@ -319,66 +332,80 @@ __global__ void sim_reset_kernel(SimConst c, SimState st, const double* __restri
 
 // ---------------------------------------------------------------- K2: lidar
 
-// xy_2_rc + distance_transform, laser_models.py:55-104 -- the exact restatement (two IEEE divisions).
-// Kept out of line and out of the hot loop: only the finishing loop of a ray whose lookup fell in the guard band calls it.
+// xy_2_rc, laser_models.py:55-86 -- the exact restatement (two IEEE divisions) on map-frame coordinates; returns the index
+// into the padded device array.  Only trace_ray_exact calls it.
 // (A float->int conversion of NaN does not give 0 on this hardware -- (int)NaN is negative -- hence the two-sided clamp.)
-__device__ __noinline__ int cell_index_exact(double x_rot, double y_rot, double res, double wres, double hres, int W, int last) {
-    int idx;
-    if (x_rot < 0 || x_rot >= wres || y_rot < 0 || y_rot >= hres) {
-        idx = last;   // (r, c) = (-1, -1): numba wraps the negative indices to dt[H-1][W-1]
+__device__ __forceinline__ int cell_index_exact(const MapView& m, double x_rot, double y_rot) {
+    int flat;
+    if (x_rot < 0 || x_rot >= m.wres || y_rot < 0 || y_rot >= m.hres) {
+        flat = m.last;   // (r, c) = (-1, -1): numba wraps the negative indices to dt[H-1][W-1]
     } else {
-        const int col = (int)(x_rot / res);
-        const int row = (int)(y_rot / res);
-        idx = row * W + col;
-        idx = idx < 0 ? 0 : (idx > last ? last : idx);   // memory safety for NaN poses / the 1-ulp wres edge
+        const int col = (int)(x_rot / m.res);
+        const int row = (int)(y_rot / m.res);
+        // numba indexes the flat buffer unchecked: col == W (x_rot one ulp under W*res) lands on the next row's first cell.
+        // The clamp is memory safety for NaN poses.
+        flat = row * m.W + col;
+        flat = flat < 0 ? 0 : (flat > m.last ? m.last : flat);
     }
-    return idx;
+    const int row = flat / m.W;
+    return (row + 1) * m.pitch + (flat - row * m.W) + 1;   // the map sits at [1 + r][1 + c] of the padded array
 }
 
-// Cell index without the two fp64 divisions.  q = x_rot * (2^F / res) is the quotient in 2^-F cell units, F = m.fx_bits
-// (fl(x*inv)*2^F == fl(x*(inv*2^F)): scaling by a power of two commutes with rounding).  Its error against the true
-// quotient is < 2.3e-16 relative, i.e. < 1e-6 units since q < 2^32, and the reference's own rounded quotient is within
-// half an ulp of the true one, so whenever the F fractional bits are at least one unit away from both cell edges,
-// trunc(q) >> F is exactly the reference's int(x_rot/res) and (q < W << F) is exactly its in-map test.  Everything
-// else -- the 2/2^F of lookups next to a cell edge, the map border, negative (converts to 0), huge (0xFFFFFFFF) and NaN
-// (0 or 0x80000000: fraction 0 either way) coordinates -- is not decided here: fast_cell returns false and the caller takes
-// the exact path.
-template <bool IDENT>
-__device__ __forceinline__ void map_frame(const MapView& m, double x, double y, double& x_rot, double& y_rot) {
-    const double x_trans = x - m.ox;
-    const double y_trans = y - m.oy;
-    if (IDENT) {          // orig_c == 1, orig_s == 0: x*1 + y*0 == x and -x*0 + y*1 == y exactly
-        x_rot = x_trans; y_rot = y_trans;
-    } else {
-        x_rot = x_trans * m.oc + y_trans * m.os;
-        y_rot = -x_trans * m.os + y_trans * m.oc;
+// trace_ray, laser_models.py:106-146, in the reference's own arithmetic from the ray's first lookup: world-frame march,
+// translate and rotate per lookup.  Out of line: the lidar kernel calls it for the few rays per hundred thousand whose fast
+// march met a lookup it could not decide (guard band, map border and beyond, non-finite coordinates).  Such a ray may be
+// the longest of its launch, so this path must not be slow either: a lookup's cell is still taken from the fixed-point
+// conversion of THIS lookup's exact map-frame position (one multiply-add away from the reference's quotient: < 1e-5
+// units, no accumulated drift) whenever its fraction clears the guard band, and only the others -- and the lookups that
+// land on a sentinel, i.e. off the map -- pay the reference's two IEEE divisions.
+// -> (total distance before the clamp to max_range, number of lookups)
+__device__ __noinline__ double2 trace_ray_exact(const MapView& m, const SimConst& c, const StepScratch& sc, unsigned s, int ti) {
+    double x = sc.scan_x[s], y = sc.scan_y[s];
+    const double sn = __ldg(c.sines + ti), cs = __ldg(c.cosines + ti);
+    const double eps = c.eps, max_range = c.max_range;
+    double total = 0.0;
+    unsigned n = 0;
+    for (;;) {
+        const double x_trans = x - m.ox;
+        const double y_trans = y - m.oy;
+        const double x_rot = x_trans * m.oc + y_trans * m.os;
+        const double y_rot = -x_trans * m.os + y_trans * m.oc;
+        const unsigned ux = __double2uint_rz(x_rot * m.inv_fx + m.fx_off);
+        const unsigned uy = __double2uint_rz(y_rot * m.inv_fx + m.fx_off);
+        double d = -1.0;
+        if ((~ux & m.guard_mask) != 0u && (~uy & m.guard_mask) != 0u)
+            d = __ldg(m.dt + ((int)(uy >> m.fx_bits) * m.pitch + (int)(ux >> m.fx_bits)));
+        if (d < 0.0) d = __ldg(m.dt + cell_index_exact(m, x_rot, y_rot));
+        total += d;
+        ++n;
+        if (!(d > eps && total <= max_range)) break;
+        x += d * cs;
+        y += d * sn;
     }
-}
-
-__device__ __forceinline__ bool fast_cell(const MapView& m, double x_rot, double y_rot, int& idx) {
-    const unsigned ux = __double2uint_rz(x_rot * m.inv_fx);
-    const unsigned uy = __double2uint_rz(y_rot * m.inv_fx);
-    idx = (int)(uy >> m.fx_bits) * m.W + (int)(ux >> m.fx_bits);
-    // (f - 1) <= mask - 2  <=>  1 <= f <= mask - 1 for the fraction f
-    return ((ux & m.fx_mask) - 1u) <= m.fx_mask - 2u && ((uy & m.fx_mask) - 1u) <= m.fx_mask - 2u && ux < m.w_fx && uy < m.h_fx;
+    return make_double2(total, (double)n);
 }
 
 // Philox2x32-10 (Salmon et al. 2011), counter-based: no per-ray generator state in HBM.  One call yields the
-// 64 bits one Box-Muller sample needs, at half the integer multiplies of Philox4x32.
-__device__ __forceinline__ uint2 philox2x32_10(uint2 ctr, uint32_t key) {
+// 64 bits one Box-Muller sample needs, at half the integer multiplies of Philox4x32.  The ten round keys
+// (key + r * 0x9E3779B9) come precomputed from the host.
+__device__ __forceinline__ uint2 philox2x32_10(uint2 ctr, const uint32_t (&key)[10]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi = __umulhi(0xD256D193u, ctr.x), lo = 0xD256D193u * ctr.x;
-        ctr = make_uint2(hi ^ key ^ ctr.y, lo);
-        key += 0x9E3779B9u;
+        ctr = make_uint2(hi ^ key[r] ^ ctr.y, lo);
     }
     return ctr;
 }
 
+// N(0, 1) from 48 random bits, Box-Muller on the SFU: u1, u2 in (0, 1) with 24 bits each, sqrt(-2 ln u1) cos(2 pi u2)
+// through lg2.approx / sqrt.approx / cos.approx (relative errors ~1e-6: far below the 1 % noise the sample scales).
 __device__ __forceinline__ float gaussian_from_bits(uint32_t a, uint32_t b) {
-    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
-    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
+    const float u1 = fmaf((float)(a >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
+    const float u2 = fmaf((float)(b >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
+    float l2, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * l2));   // -2 ln 2 * log2(u1)
+    return rad * __cosf(6.28318530717958647692f * u2);
 }
 
 // n / d for a run-time d through the multiply-shift pair the host precomputed (Granlund & Montgomery 1994)
@@ -387,181 +414,339 @@ __device__ __forceinline__ unsigned fast_div(unsigned n, FastDiv d) {
     return (t + ((n - t) >> d.sh1)) >> d.sh2;
 }
 
-// _pack_flat_obs lidar channel, f110_env.py:557-560
-__device__ __forceinline__ float obs_lidar(double range, float lm) {
+// _pack_flat_obs lidar channel, f110_env.py:557-560: clip(nan_to_num(float32(range)), 0, lm) / lm
+// FAST: lm == 30.0f.  rf / 30 through the reciprocal and two fused corrections equals the IEEE quotient for every
+// float in [2^-120, 30] and for 0 (all 1 106 247 681 bit patterns of [0, 30] checked on the host, tools/checks/div30_check.c;
+// the 279 620 mismatches all lie below 2^-125, where the quotient is subnormal) -- 3 instructions instead of ~15.
+template <bool FAST>
+__device__ __forceinline__ float obs_lidar(double range, float lm, float rcp) {
     float rf = (float)range;
     if (rf != rf) rf = lm;
     else if (isinf(rf)) rf = rf > 0 ? lm : 0.0f;
     rf = rf < 0.0f ? 0.0f : rf;
     rf = rf > lm ? lm : rf;
+    if (FAST && (rf == 0.0f || rf >= 7.5e-37f)) {
+        const float q0 = rf * rcp;
+        return fmaf(fmaf(-q0, lm, rf), rcp, q0);
+    }
     return rf / lm;
 }
 
-#ifndef HEAVY_ITERS
-#define HEAVY_ITERS 48u
+// A unit's class for the next step's launch order, from the longest ray (in lookups) of its 32
+#ifndef HEAVY_T0
+#define HEAVY_T0 96u
 #endif
-#ifndef LIDAR_MAX_THREADS
-#define LIDAR_MAX_THREADS 128
+#ifndef HEAVY_T1
+#define HEAVY_T1 48u
 #endif
+#ifndef HEAVY_T2
+#define HEAVY_T2 24u
+#endif
+constexpr int LIDAR_THREADS = 128;
 #ifndef LIDAR_MIN_BLOCKS
 #define LIDAR_MIN_BLOCKS 12
 #endif
-// COUNT : count dt lookups (roofline L-bar)            IDENT : map origin yaw == 0
-// DIRECT: A == 1 (env == s, no opponent ray-cast can follow, no fp64 scratch copy of the scan)
-template <bool COUNT, bool IDENT, bool DIRECT>
-__global__ void __launch_bounds__(LIDAR_MAX_THREADS, LIDAR_MIN_BLOCKS) lidar_kernel(SimConst c, MapView m, SimState st, StepScratch sc, F110StepIO io) {
+#ifndef LIDAR_CHUNK_OVERRIDE
+#define LIDAR_CHUNK_OVERRIDE 4
+#endif
+constexpr unsigned LIDAR_CHUNK = LIDAR_CHUNK_OVERRIDE;   // queue positions a warp takes per fetch in the bulk of the light region
+
+// K2.  One thread per beam; a UNIT is 32 consecutive beams of one scan (the last unit of a scan is partly empty: 1080
+// beams = 33.75 units), so everything that belongs to the scan -- its start in map coordinates, theta index, speed, noise
+// counter, which K1 left in one 32-byte ScanHead -- is one broadcast load per warp.  A warp takes units from a device-wide
+// queue until it is empty.
+//
+// * The march (trace_ray, laser_models.py:129-144) runs in FIXED-POINT MAP COORDINATES: X = x_rot * 2^F / res is advanced
+//   by d * DX per step, DX = (direction rotated into the map frame) * 2^F / res read from a table set_map prepared,
+//   instead of being recomputed from the world-frame position: no translate / rotate / scale per lookup (4 fp64
+//   operations, 2 of them on the dependent chain), no in-map test (the map is padded with sentinels, see MapView).
+//   X drifts from the reference's own rounded quotient by < 2e-6 fixed-point units per step (both are roundings of the
+//   same real recurrence as long as they have visited the same cells, and every product and sum involved is below 2^32
+//   with a 2^-53 relative rounding), so after any number of steps a ray can take (total <= 30 m in steps > 1e-4 m:
+//   < 3e5) the two are less than one unit apart.  A lookup whose fixed-point fraction is at least m.guard (>= 2) units
+//   away from both cell edges therefore addresses exactly the reference's cell; since every d read is then the
+//   reference's, `total` is the reference's bit for bit.  The coordinates carry an offset of one cell minus the guard, so
+//   that the guard test is one mask per axis (fraction's upper bits all set <=> within guard of either edge).  Any other
+//   lookup is not decided here: negative and NaN coordinates convert to 0 (row / column 0 of the padded map: sentinels),
+//   huge ones to 0xFFFFFFFF (inside the guard band), a coordinate beyond the map reads a sentinel, and in each case the
+//   ray is redone from its first lookup by trace_ray_exact.
+// * TUNED variants (FB = the map's fraction bits as a compile-time constant, for 19..22 bits = maps of 1 023 to 8 190 cells
+//   a side; default eps test; lidar_max 30): ptxas re-loads every kernel parameter the loop uses from the constant bank
+//   on EVERY iteration (7 of 30 instructions, and for a lone long ray their latency sits on the dependent chain: 590
+//   cycles per lookup measured, against 270 for the L2 hit itself).  With the shifts, masks and pitch as immediates, the
+//   eps test as d > 0 (valid when the smallest positive cell exceeds eps, which set_map checks) and max_range = 30 as an
+//   immediate too, the loop has no constant load left (ptxas cannot be talked out of them: values made opaque with a
+//   zero it cannot know are still re-derived inside the loop, whatever the register budget).  The generic variant (FB = 0) handles everything else,
+//   and counts lookups for the roofline.
+// * Persistent warps (the grid is one wave: SMs x resident CTAs).  With one CTA per 128 rays a CTA's slot is only
+//   re-used when its slowest warp is through, and ray lengths are heavy-tailed (median 4 lookups, p99 42, max ~300 on
+//   the Shanghai map): 60 % of the warp slots were occupied where the register file allows 75 %.
+// * Longest-first order.  A ray's length changes little from one step to the next, so every unit is classed by its
+//   longest ray (>= 96 / 48 / 24 lookups, else light) and the next step's queue serves the three heavy lists first, then
+//   the light units in natural order (skipping the listed ones).  The kernel's tail is then made of light units.
+//   Only the order depends on this history, never a result.  The lists are double-buffered by a parity word in device
+//   memory which the post kernel flips, so a captured CUDA graph replays correctly.  The units of an env that K1 has just
+//   reset have no usable history: K1 appends them to the third list (see dynamics_kernel).
+// * The queue is one atomic counter (same-address atomics retire at about one per ns on this part: one fetch per unit
+//   costs 45 % at 32 768 envs); a fetch takes up to LIDAR_CHUNK positions at a time in the bulk of the light region, one
+//   near the ends, and is issued after the march of the chunk's last unit, so that its latency hides behind the epilogue.
+template <int FB, bool COUNT, bool DIRECT>
+__global__ void __launch_bounds__(LIDAR_THREADS, LIDAR_MIN_BLOCKS)
+lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView m, const __grid_constant__ SimState st,
+             const __grid_constant__ StepScratch sc, const __grid_constant__ F110StepIO io) {
+    constexpr bool TUNED = FB != 0;
     cudaGridDependencySynchronize();   // PDL: everything below reads what the dynamics kernel (and the previous step) wrote
-    const unsigned total = (unsigned)c.NA * (unsigned)c.B;
-    // ---- work-unit selection (one unit = 32 consecutive rays = one warp).  Ray lengths are heavy-tailed (median 4
-    // lookups, p99 42, max ~300 on the Shanghai map), so a long ray that starts in the last wave of CTAs leaves
-    // most SMs idle while it finishes.  A ray's length changes little from one step to the next, so every warp
-    // records whether its unit was long (>= HEAVY_ITERS lookups) and the next step's grid runs those units FIRST,
-    // in a front region of sc.front_units warps (the post kernel latches the count, the dynamics kernel publishes the
-    // list); the remaining warps walk the units in natural order and skip the ones the front region took.  Only the
-    // launch order depends on this history, never a result.
-    const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
-    unsigned unit;
-    if (gwarp < sc.front_units) {
-        if (gwarp >= sc.heavy_cnt[0]) return;
-        unit = sc.heavy_list[gwarp];
-    } else {
-        unit = gwarp - sc.front_units;
-        if (unit >= sc.num_units) return;
-        if (sc.unit_heavy[unit]) return;
-    }
-    const unsigned r = unit * 32u + lane;
-    unsigned nlook = 0;
-    bool live = r < total;
-    unsigned s = 0, i = 0;
-    unsigned env = 0;
-    if (live) {
-        s = fast_div(r, c.div_B);
-        i = r - s * (unsigned)c.B;
-        env = DIRECT ? s : fast_div(s, c.div_A);
-        if (io.active_mask && !io.active_mask[env]) live = false;
-    }
-    if (live) {
-        // beam direction: closed form of the reference's running sum theta_index += increment with wrap
-        // (laser_models.py:174-184).  The running sum differs from the closed form by < 1.3e-10 after
-        // 1080 adds; only when the value sits within 1e-9 of an integer can int() disagree, and then the
-        // sum is replayed exactly.
-        const double t0 = sc.theta0[s];
-        const double td = (double)c.theta_dis;
-        double t = t0 + (double)i * c.theta_inc;
-        if (t >= td) t -= td;
-        if (fabs(t - rint(t)) < 1e-9) {
-            t = t0;
-            for (unsigned k = 0; k < i; ++k) {
-                t += c.theta_inc;
-                while (t >= td) t -= td;
-            }
-        }
-        int ti = (int)t;
-        // memory safety only: a NaN yaw (a car poisoned by a NaN command) converts to a NEGATIVE index on this hardware
-        ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
-        const double sn = __ldg(c.sines + ti);
-        const double cs = __ldg(c.cosines + ti);
+    const unsigned nwarps = gridDim.x * (LIDAR_THREADS / 32);
+    const unsigned epoch = sc.ctrl[CTRL_EPOCH];
+    const unsigned par = epoch & 1u;
+    // A processed unit's class word is set to `done`; the array then serves as the next step's recording array (heavier
+    // classes overwrite it by atomicMin) and comes back two steps later, when `done` is the other of the two values:
+    // whatever is >= 3 and not this step's `done` is a light unit that has not been processed yet.
+    const unsigned done = 4u + ((epoch >> 1) & 1u);
+    // list ends (K1 may have pushed the third count past its capacity)
+    const unsigned n0 = sc.ctrl[CTRL_CUR], n1 = n0 + sc.ctrl[CTRL_CUR + 1], n2 = n1 + min(sc.ctrl[CTRL_CUR + 2], sc.cap[2]);
+    const unsigned npos = n2 + sc.num_units;
+    const unsigned cap0 = sc.cap[0], cap1 = sc.cap[1], cap2 = sc.cap[2];
+    const unsigned* __restrict__ cur_list = sc.list[par];
+    unsigned* cur_cls = sc.cls[par];
+    unsigned* __restrict__ next_list = sc.list[par ^ 1u];
+    unsigned* __restrict__ next_cls = sc.cls[par ^ 1u];
+    unsigned* qpos = sc.ctrl + CTRL_POS;
+    unsigned cnt_look = 0, cnt_rays = 0, cnt_max = 0, cnt_redone = 0;
 
-        // trace_ray, laser_models.py:129-144
-        double x = sc.scan_x[s], y = sc.scan_y[s];
-        const double eps = c.eps, max_range = c.max_range;
-        // The hot loop holds only the guarded fixed-point lookup and no call: a lookup that lands in the guard band
-        // leaves it for good and the ray is finished by the second loop, in the reference's own arithmetic (two IEEE
-        // divisions per lookup).  A call inside the hot loop costs 5 % of the kernel: everything live across it has to
-        // sit in callee-saved registers or be re-read, lookup after lookup, for a path 4 in 2^21 lookups take.
-        double x_rot, y_rot, d = 1.0, total_d = 0.0;
-        int idx;
-        map_frame<IDENT>(m, x, y, x_rot, y_rot);
-        bool fast = fast_cell(m, x_rot, y_rot, idx);
-        while (fast) {
-            d = __ldg(m.dt + idx);
-            total_d += d;
-            ++nlook;
-            if (!(d > eps && total_d <= max_range)) break;
-            x += d * cs;
-            y += d * sn;
-            map_frame<IDENT>(m, x, y, x_rot, y_rot);
-            fast = fast_cell(m, x_rot, y_rot, idx);
+    // position -> unit: an entry of list b, valid if b is still the unit's class (a unit can have been entered on a lighter
+    // list before a neighbour raised it to a heavier one), or, in the light region, the unit itself if its class is light
+    auto resolve = [&](unsigned p, unsigned& unit, bool& skip) {
+        unit = 0u; skip = true;
+        if (p < n2) {
+            const unsigned b = p < n0 ? 0u : (p < n1 ? 1u : 2u);
+            const unsigned k = p < n0 ? p : (p < n1 ? cap0 + (p - n0) : cap0 + cap1 + (p - n1));
+            unit = cur_list[k];
+            skip = cur_cls[unit] != b;
+        } else if (p < npos) {
+            unit = p - n2;
+            skip = false;
+            if (sc.ordered) { const unsigned v = cur_cls[unit]; skip = v < 3u || v == done; }
         }
-        if (!fast) {
-            for (;;) {
-                d = __ldg(m.dt + cell_index_exact(x_rot, y_rot, m.res, m.wres, m.hres, m.W, m.last));
-                total_d += d;
-                ++nlook;
-                if (!(d > eps && total_d <= max_range)) break;
-                x += d * cs;
-                y += d * sn;
-                map_frame<IDENT>(m, x, y, x_rot, y_rot);
-            }
-        }
-        if (total_d > max_range) total_d = max_range;
+    };
 
-        // scan += noise, laser_models.py:450-452
-        double range = total_d;
-        if (io.noise) {
-            range += io.noise[r];
-        } else if (c.noise_std > 0.0) {
-            // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
-            // reset (base_classes.py:204), the stream restarts with every episode; unlike it, every ray has its own
-            const uint2 bits = philox2x32_10(make_uint2(r, st.step_count[env]), c.noise_key);
-            range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
-        }
-        // The scan goes straight to the caller's buffers.  With opponents (A >= 2) the post kernel lowers the few beams
-        // that hit another car afterwards, from the fp64 copy kept in scratch.
-        // Streaming stores (evict-first): nothing in this kernel reads the outputs back, and at 32 768 envs the 142 MB of
-        // observations would otherwise push the map out of L2 (2.5 % of the kernel there).
-        if (io.scans_f64) __stcs(io.scans_f64 + r, range);
-        if (io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
-        if (DIRECT) {
-            if (io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar(range, c.lidar_max));
+    // the first position of every warp is its own index: the counter starts at 0 and a fetch returns old + nwarps
+    unsigned pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, end = pos + 1u;
+    unsigned f = 0, take = 1u;
+    // guided self-scheduling: half of an even share of what is left, between 1 and LIDAR_CHUNK positions; one at a time in
+    // the heavy lists, where a unit is long and balance matters most
+    auto fetch = [&](unsigned at) {
+        take = at < n2 ? 1u : (npos - at) / (2u * nwarps);
+        take = take < 1u ? 1u : (take > (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) ? (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) : take);
+        if (lane == 0) f = atomicAdd(qpos, take) + nwarps;
+    };
+    unsigned unit; bool skip;
+    resolve(pos, unit, skip);
+    while (pos < npos) {
+        unsigned nlook = 0;
+        bool live = false;
+        unsigned npos_next, nunit; bool nskip;
+        if (!skip) {
+            unsigned t_start = 0;
+            if (COUNT) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_start));
+            // ---- the unit's scan and this lane's beam
+            const unsigned s = fast_div(unit, c.div_ups);
+            const unsigned i = (unit - s * c.ups) * 32u + lane;
+            const unsigned env = DIRECT ? s : fast_div(s, c.div_A);
+            live = i < (unsigned)c.B && !(io.active_mask && !io.active_mask[env]);
+            const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;      // the dead lanes of a scan's last unit shadow its last beam
+            const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; speed
+            const double2 bt = __ldg(c.beam_tt + ic);                            // beam cosine, side distance (check_ttc_jit)
+            const unsigned stepc = st.step_count[env];
+            // beam direction: closed form of the reference's running sum theta_index += increment with wrap
+            // (laser_models.py:174-184).  The running sum differs from the closed form by < 1.3e-10 after
+            // 1080 adds; only when the value sits within 1e-9 of an integer can int() disagree, and then the
+            // sum is replayed exactly.
+            const double td = (double)c.theta_dis;
+            double t = head.z + (double)ic * c.theta_inc;
+            if (t >= td) t -= td;
+            if (fabs(t - rint(t)) < 1e-9 || t >= td) {
+                t = head.z;
+                for (unsigned k = 0; k < ic; ++k) {
+                    t += c.theta_inc;
+                    while (t >= td) t -= td;
+                }
+            }
+            int ti = (int)t;
+            // memory safety only: a NaN yaw (a car poisoned by a NaN command) converts to a NEGATIVE index on this hardware
+            ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
+            const double2 dir = __ldg(c.dir_fx + ti);
+            // iTTC prefilter (check_ttc_jit, laser_models.py:205-213): ttc = (range - side) / (v cos) lies in [0, thresh) only
+            // if range - side <= thresh |v cos|; a range above ttc_lim = side + 2.5 thresh |v cos| (the margin swallows every
+            // rounding here) cannot hit, and neither can a car at rest (the reference tests vel != 0 first).  NaNs compare
+            // false and fall through to the exact test.
+            const double ttc_lim = head.w != 0.0 ? bt.y + 2.5 * c.ttc_thresh * fabs(head.w * bt.x) : -INFINITY;
+
+            // ---- the march
+            double X = head.x, Y = head.y, total_d = 0.0, d = 0.0;
+            {
+                const unsigned fb = TUNED ? (unsigned)FB : m.fx_bits;
+                const unsigned gm = TUNED ? (((1u << FB) - 1u) & ~3u) : m.guard_mask;
+                const int pitch = TUNED ? (1 << (32 - FB)) + 16 : m.pitch;
+                const double eps = c.eps;
+                const double max_range = TUNED ? 30.0 : c.max_range;   // an immediate: 30.0 has no low mantissa word
+                const double* __restrict__ dt = m.dt;
+                // The loop is software-pipelined by one lookup: the cell of the NEXT position is loaded before it is known
+                // whether the ray goes on (any 32-bit fixed-point coordinate addresses a cell of the padded array, so the
+                // load is always safe).  The dependent chain of a lookup is then load -> multiply-add -> convert -> index ->
+                // load; the range / eps / guard tests run beside the load instead of in front of it.  Cost: one extra
+                // lookup per ray.
+                bool decided = true;
+                if (live) {
+                    unsigned ux = __double2uint_rz(X), uy = __double2uint_rz(Y);
+                    unsigned tx, ty;
+                    // fraction's upper bits all ones <=> within guard of a cell edge (MapView.fx_off).  (~u & gm) != 0 as one
+                    // LOP3 with a predicate result each; written in C, NVVM turns it into (u & gm) != gm: two instructions
+                    asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));
+                    asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
+                    decided = tx != 0u && ty != 0u;
+                    if (decided) {
+                        d = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));
+                        for (;;) {
+                            X += d * dir.x;
+                            Y += d * dir.y;
+                            ux = __double2uint_rz(X);
+                            uy = __double2uint_rz(Y);
+                            const double d_next = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));
+                            total_d += d;
+                            ++nlook;
+                            if (!((TUNED ? d > 0.0 : d > eps) && total_d <= max_range)) break;
+                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));
+                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
+                            decided = tx != 0u && ty != 0u;
+                            if (!decided) break;
+                            d = d_next;
+                        }
+                    }
+                }
+                if (live && (!decided || d < 0.0)) {
+                    const double2 ex = trace_ray_exact(m, c, sc, s, ti);
+                    total_d = ex.x;
+                    nlook = (unsigned)ex.y;
+                    if (COUNT) ++cnt_redone;
+                }
+                if (total_d > c.max_range) total_d = c.max_range;
+            }
+
+            // ---- the next position: inside the chunk, what it holds is loaded now and arrives while the epilogue runs; at
+            // the end of a chunk the fetch is issued now and resolved after the epilogue.  (Not earlier: a position reserved
+            // at the start of a unit waits for that unit, and behind a 70 us unit sat positions handed out at 5 us.)
+            npos_next = pos + 1u;
+            const bool chunk_end = npos_next >= end;
+            if (chunk_end) fetch(pos);
+            else resolve(npos_next, nunit, nskip);
+
+            if (live) {
+                // scan += noise, laser_models.py:450-452
+                const unsigned r = s * (unsigned)c.B + i;
+                double range = total_d;
+                if (io.noise) {
+                    range += io.noise[r];
+                } else if (c.noise_std > 0.0) {
+                    // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
+                    // reset (base_classes.py:204), the stream restarts with every episode; unlike it, every ray has its own
+                    const uint2 bits = philox2x32_10(make_uint2(r, stepc), c.philox_key);
+                    range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
+                }
+                // The scan goes straight to the caller's buffers.  With opponents (A >= 2) the post kernel lowers the few
+                // beams that hit another car afterwards, from the fp64 copy kept in scratch.
+                // Streaming stores (evict-first): nothing in this kernel reads the outputs back, and at 32 768 envs the
+                // 142 MB of observations would otherwise push the map out of L2 (2.5 % of the kernel there).
+                if (io.scans_f64) __stcs(io.scans_f64 + r, range);
+                if (io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
+                if (DIRECT) {
+                    if (io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
+                } else {
+                    sc.scan[r] = range;
+                    if (io.obs && s == env * (unsigned)c.A)
+                        __stcs(io.obs + (size_t)env * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
+                }
+                // check_ttc_jit (any-reduction; the reference's early break is irrelevant)
+                if (!(range > ttc_lim)) {
+                    // (rare: re-read rather than keep four registers alive across the march)
+                    const double2 bt2 = __ldg(c.beam_tt + i);
+                    const double ttc = (range - bt2.y) / (sc.head[4u * s + 3u] * bt2.x);
+                    if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
+                }
+            }
+            // ---- history for the next step's launch order.  The class goes to the unit AND its two neighbours in the scan: a
+            // long (wall-grazing) ray wanders across the beam index as the car yaws, and the unit it moves into has no
+            // history of its own -- 22 units per step with >= 48 lookups were predicted light, the longest ~120 lookups;
+            // with the neighbours 0.1 and ~27 (4096-env C3 workload, 60 steps recorded).  Lanes 0..2 do one target each.
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, nlook);
+            if (lane == 3u && sc.ordered) cur_cls[unit] = done;
+            if (wmax >= HEAVY_T2 && lane < 3u && sc.ordered) {
+                const unsigned b = wmax >= HEAVY_T0 ? 0u : (wmax >= HEAVY_T1 ? 1u : 2u);
+                const unsigned k = unit - s * c.ups;
+                const bool in_scan = lane == 1u || (lane == 0u ? k > 0u : k + 1u < c.ups);
+                if (in_scan) {
+                    const unsigned u = unit + lane - 1u;
+                    if (atomicMin(next_cls + u, b) > b) {      // this call made b the unit's class: enter it on list b
+                        const unsigned slot = atomicAdd(sc.ctrl + CTRL_NEXT + b * CTRL_NEXT_STRIDE, 1u);
+                        if (slot < (b == 0 ? cap0 : (b == 1 ? cap1 : cap2))) next_list[(b == 0 ? 0u : (b == 1 ? cap0 : cap0 + cap1)) + slot] = u;
+                        else atomicMax(next_cls + u, 3u);      // list full: back to light (whatever others do next stays consistent)
+                    }
+                }
+            }
+            if (chunk_end) {
+                npos_next = __shfl_sync(0xffffffffu, f, 0);
+                end = npos_next + take;
+                resolve(npos_next, nunit, nskip);
+            }
+            if (COUNT) {
+                if (sc.timeline && lane == 0) {
+                    unsigned t_end, smid;
+                    asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_end));
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    sc.timeline[unit] = make_uint4(t_start, t_end, wmax, (smid << 24) | (pos & 0xFFFFFFu));
+                }
+                cnt_look += nlook;
+                cnt_rays += live ? 1u : 0u;
+                cnt_max = max(cnt_max, nlook);
+            }
         } else {
-            sc.scan[r] = range;
-            if (io.obs && s == env * (unsigned)c.A) __stcs(io.obs + (size_t)env * (c.B + 8) + i, obs_lidar(range, c.lidar_max));
+            npos_next = pos + 1u;
+            if (npos_next >= end) { fetch(pos); npos_next = __shfl_sync(0xffffffffu, f, 0); end = npos_next + take; }
+            resolve(npos_next, nunit, nskip);
         }
-
-        // check_ttc_jit, laser_models.py:205-213 (any-reduction; the reference's early break is irrelevant)
-        const double vel = st.x[3][s];
-        if (vel != 0.0) {
-            const double proj_vel = vel * __ldg(c.beam_cos + i);
-            const double num = range - __ldg(c.side_dist + i);
-            // |ttc| > 2*thresh whenever num > 2*thresh*|proj_vel|: then ttc is either >= thresh or negative and the
-            // exact quotient need not be formed (the negation keeps NaNs on the exact path)
-            if (!(num > 2.0 * c.ttc_thresh * fabs(proj_vel))) {
-                const double ttc = num / proj_vel;
-                if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
-            }
-        }
-    }
-    // ---- history for the next step's launch order
-    const unsigned wmax = __reduce_max_sync(0xffffffffu, nlook);
-    if (lane == 0) {
-        bool heavy = wmax >= HEAVY_ITERS;
-        if (heavy) {
-            const unsigned slot = atomicAdd(sc.heavy_cnt + 1, 1u);
-            if (slot < sc.front_units) sc.heavy_list[sc.front_units + slot] = unit;
-            else heavy = false;
-        }
-        sc.unit_heavy[sc.num_units + unit] = heavy ? 1 : 0;
+        pos = npos_next; unit = nunit; skip = nskip;
     }
     if (COUNT) {
-        const unsigned wsum = __reduce_add_sync(0xffffffffu, nlook);
-        const unsigned wrays = __popc(__ballot_sync(0xffffffffu, live));
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, cnt_look);
+        const unsigned wrays = __reduce_add_sync(0xffffffffu, cnt_rays);
+        const unsigned wmax = __reduce_max_sync(0xffffffffu, cnt_max);
+        const unsigned wredone = __reduce_add_sync(0xffffffffu, cnt_redone);
         if (lane == 0 && wrays) {
             atomicAdd(sc.lookups, (unsigned long long)wsum);
             atomicAdd(sc.lookups + 1, (unsigned long long)wrays);
             atomicMax(sc.lookups + 2, (unsigned long long)wmax);   // longest ray seen so far
+            if (wredone) atomicAdd(sc.lookups + 3, (unsigned long long)wredone);
         }
     }
 }
 
 // ---------------------------------------------------------------- K3: post
 
-// the lidar kernel of this step is complete: latch how many heavy units it recorded and re-arm the counter
+// End of a step's lidar bookkeeping, done by the post kernel: the last block to finish (ticket counter) latches the
+// recorded counts, flips the parity and rewinds the queue.
 __device__ __forceinline__ void latch_launch_order(const StepScratch& sc) {
-    const unsigned n = sc.heavy_cnt[1];
-    sc.heavy_cnt[0] = n < sc.front_units ? n : sc.front_units;
-    sc.heavy_cnt[1] = 0u;
+    __threadfence();
+    if (threadIdx.x != 0) return;
+    if (atomicAdd(sc.ctrl + CTRL_TICKET, 1u) != gridDim.x - 1u) return;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const unsigned n = atomicExch(sc.ctrl + CTRL_NEXT + b * CTRL_NEXT_STRIDE, 0u);
+        sc.ctrl[CTRL_CUR + b] = n < sc.cap[b] ? n : sc.cap[b];
+    }
+    sc.ctrl[CTRL_EPOCH] += 1u;
+    sc.ctrl[CTRL_POS] = 0u;
+    sc.ctrl[CTRL_TICKET] = 0u;
 }
 
 // get_trmtx + get_vertices, collision_models.py:218-260; order rl, rr, fr, fl
@@ -742,7 +927,6 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     const int tid = threadIdx.x;
     const int epc = post_envs_per_cta(A);
     const int env0 = blockIdx.x * epc;
-    if (blockIdx.x == 0 && tid == 0) latch_launch_order(sc);
     extern __shared__ double s_dyn[];
     const int stride = post_smem_doubles(A);
     __shared__ int s_active[16];
@@ -931,7 +1115,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
                     sc.scan[g] = range;
                     if (io.scans_f64) io.scans_f64[g] = range;
                     if (io.scans_f32) io.scans_f32[g] = (float)range;
-                    if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar(range, lm);
+                    if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar<false>(range, lm, 0.0f);
                 }
             }
         }
@@ -970,6 +1154,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
             if (all_laps) atomicAdd(sc.stats + F110_STAT_LAPS_DONE, 1.0);
         }
     }
+    latch_launch_order(sc);
 }
 
 // K3 for A == 1: nothing to ray-cast and no pair to test, the lidar kernel already wrote the scans -> one thread
@@ -977,9 +1162,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
 __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     cudaGridDependencySynchronize();
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env == 0) latch_launch_order(sc);
-    if (env >= c.N) return;
-    if (io.active_mask && !io.active_mask[env]) return;
+    if (env < c.N && !(io.active_mask && !io.active_mask[env])) {
     const int s = env;
     const int hit = sc.ttc_hit[s];
     const double px = st.x[0][s], py = st.x[1][s];
@@ -1032,6 +1215,8 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
         if (hit) atomicAdd(sc.stats + F110_STAT_EGO_COLLISIONS, 1.0);
         if (tog >= 4) atomicAdd(sc.stats + F110_STAT_LAPS_DONE, 1.0);
     }
+    }
+    latch_launch_order(sc);
 }
 
 }  // namespace
@@ -1039,52 +1224,114 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
 // Launch with programmatic stream serialisation (PDL): the grid may be scheduled while the previous kernel of the stream
 // drains; the kernel itself waits in cudaGridDependencySynchronize() before it touches anything that kernel wrote.
 template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-void launch_dynamics(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
+cudaError_t launch_dynamics(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     const int threads = 128;
-    launch_pdl(dynamics_kernel, dim3((c.NA + threads - 1) / threads), dim3(threads), 0, s, c, st, sc, io);
+    return launch_pdl(dynamics_kernel, dim3((c.NA + threads - 1) / threads), dim3(threads), 0, s, c, m, st, sc, io);
 }
 
-template <bool COUNT, bool IDENT>
-static void launch_lidar_t(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc,
-                           const F110StepIO& io, unsigned blocks, unsigned threads, cudaStream_t s) {
-    if (c.A == 1) launch_pdl(lidar_kernel<COUNT, IDENT, true>, dim3(blocks), dim3(threads), 0, s, c, m, st, sc, io);
-    else launch_pdl(lidar_kernel<COUNT, IDENT, false>, dim3(blocks), dim3(threads), 0, s, c, m, st, sc, io);
-}
+typedef void (*LidarKernel)(SimConst, MapView, SimState, StepScratch, F110StepIO);
 
-void launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
-                  bool count_lookups, int threads_per_block, cudaStream_t s) {
-    const unsigned threads = (unsigned)threads_per_block;
-    const unsigned warps = sc.front_units + sc.num_units;
-    const unsigned blocks = (warps * 32u + threads - 1) / threads;
-    const bool ident = (m.oc == 1.0 && m.os == 0.0);
-    if (count_lookups) {
-        if (ident) launch_lidar_t<true, true>(c, m, st, sc, io, blocks, threads, s);
-        else launch_lidar_t<true, false>(c, m, st, sc, io, blocks, threads, s);
-    } else {
-        if (ident) launch_lidar_t<false, true>(c, m, st, sc, io, blocks, threads, s);
-        else launch_lidar_t<false, false>(c, m, st, sc, io, blocks, threads, s);
+template <bool DIRECT>
+static LidarKernel lidar_variant_t(int fb, bool count) {
+    switch (fb) {
+        case 19: return count ? lidar_kernel<19, true, DIRECT> : lidar_kernel<19, false, DIRECT>;
+        case 20: return count ? lidar_kernel<20, true, DIRECT> : lidar_kernel<20, false, DIRECT>;
+        case 21: return count ? lidar_kernel<21, true, DIRECT> : lidar_kernel<21, false, DIRECT>;
+        case 22: return count ? lidar_kernel<22, true, DIRECT> : lidar_kernel<22, false, DIRECT>;
+        default: return count ? lidar_kernel<0, true, DIRECT> : lidar_kernel<0, false, DIRECT>;
     }
 }
-
-void launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
-    if (c.A == 1) launch_pdl(post_single_kernel, dim3((c.N + 127) / 128), dim3(128), 0, s, c, st, sc, io);
-    else {
-        const int epc = post_envs_per_cta(c.A);
-        launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS), sizeof(double) * post_smem_doubles(c.A) * epc, s, c, st, sc, io);
-    }
+// fb = the map's fraction bits when the TUNED variant applies, else 0
+static LidarKernel lidar_variant(int fb, bool count, bool direct) {
+    return direct ? lidar_variant_t<true>(fb, count) : lidar_variant_t<false>(fb, count);
 }
 
-void launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {
+// CTAs of the lidar kernel that are resident at once on the current device (one wave of persistent warps)
+int lidar_resident_blocks(bool single_agent) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lidar_variant(21, false, single_agent), LIDAR_THREADS, 0) != cudaSuccess)
+        return -1;
+    return sms * per_sm;
+}
+
+cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
+                         bool count_lookups, int resident_blocks, cudaStream_t s) {
+    // TUNED variant: compile-time fraction bits, d > 0 for d > eps, max_range 30, the observation's division by 30 through its reciprocal
+    const bool tuned = m.guard == 2u && c.obs_fast_div && c.max_range == 30.0 && c.eps > 0.0 && m.min_positive > c.eps &&
+                       m.fx_bits >= 19u && m.fx_bits <= 22u;
+    // one wave of persistent warps, or fewer when there are not that many units
+    const unsigned want = (sc.num_units + LIDAR_THREADS / 32 - 1) / (LIDAR_THREADS / 32);
+    const unsigned blocks = want < (unsigned)resident_blocks ? want : (unsigned)resident_blocks;
+    return launch_pdl(lidar_variant(tuned ? (int)m.fx_bits : 0, count_lookups, c.A == 1), dim3(blocks ? blocks : 1u), dim3(LIDAR_THREADS), 0,
+                      s, c, m, st, sc, io);
+}
+
+cudaError_t launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
+    if (c.A == 1) return launch_pdl(post_single_kernel, dim3((c.N + 127) / 128), dim3(128), 0, s, c, st, sc, io);
+    const int epc = post_envs_per_cta(c.A);
+    return launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS), sizeof(double) * post_smem_doubles(c.A) * epc, s, c, st, sc, io);
+}
+
+cudaError_t launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {
     const int threads = 128;
     sim_reset_kernel<<<(c.NA + threads - 1) / threads, threads, 0, s>>>(c, st, poses, mask);
+    return cudaPeekAtLastError();
+}
+
+// ---------------------------------------------------------------- map padding (set_map time, off the step path)
+
+namespace {
+__global__ void pad_map_kernel(const double* __restrict__ dense, int H, int W, double* __restrict__ padded, int prows, int pitch) {
+    const size_t n = (size_t)prows * pitch;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(k / pitch) - 1, col = (int)(k - (size_t)(row + 1) * pitch) - 1;
+        padded[k] = (row >= 0 && row < H && col >= 0 && col < W) ? dense[(size_t)row * W + col] : -1.0;
+    }
+}
+
+// doubles that are > 0 order like their bit patterns: atomicMin on the bits finds the smallest positive cell
+__global__ void min_positive_kernel(const double* __restrict__ dense, size_t n, unsigned long long* out) {
+    unsigned long long best = 0x7FF0000000000000ull;   // +inf
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const double v = dense[k];
+        if (v > 0.0) { const unsigned long long b = (unsigned long long)__double_as_longlong(v); best = b < best ? b : best; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(out, best);
+}
+}  // namespace
+
+cudaError_t launch_pad_map(const double* dense, int H, int W, double* padded, int prows, int pitch, cudaStream_t s) {
+    pad_map_kernel<<<148 * 8, 256, 0, s>>>(dense, H, W, padded, prows, pitch);
+    return cudaPeekAtLastError();
+}
+
+cudaError_t map_min_positive(const double* dense, size_t cells, double* out, cudaStream_t s) {
+    unsigned long long* d = nullptr;
+    const unsigned long long inf = 0x7FF0000000000000ull;
+    cudaError_t e = cudaMalloc(&d, sizeof(*d));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(d, &inf, sizeof(inf), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) { min_positive_kernel<<<148 * 4, 256, 0, s>>>(dense, cells, d); e = cudaPeekAtLastError(); }
+    unsigned long long h = inf;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    memcpy(out, &h, sizeof(h));
+    return e;
 }

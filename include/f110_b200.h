@@ -192,6 +192,17 @@ int f110_get_stats(F110Sim* sim, double* out, int32_t reset, void* stream);
 int f110_get_lookup_count(F110Sim* sim, uint64_t* lookups, uint64_t* rays);
 /* Longest ray (in lookups) seen so far, as of the last f110_get_lookup_count call. */
 int64_t f110_max_lookups(const F110Sim* sim);
+/* Rays the lidar kernel redid in the reference's own arithmetic because its fixed-point march met a lookup it could not
+ * decide (cell-edge guard band, map border and beyond, non-finite pose), as of the last f110_get_lookup_count call. */
+int64_t f110_redone_rays(const F110Sim* sim);
+/* Development aid (requires F110_FLAG_COUNT_LOOKUPS): per work unit of the last lidar launch, 4 words (start ns, end ns,
+ * both the low half of %globaltimer; longest ray in lookups; sm << 24 | queue position).  out == NULL returns the number
+ * of units (0 when no timeline is kept); otherwise copies [units][4] words and returns the count, or a negative error. */
+int64_t f110_debug_unit_timeline(F110Sim* sim, uint32_t* out, int64_t capacity_units);
+/* Incremented by every successful f110_set_map / f110_set_map_image.  The step kernels receive the map descriptor by
+ * value, so a CUDA graph captured from f110_step before a map change still holds the old (freed) map: re-capture when
+ * this number has changed (F110VecEnv does). */
+int64_t f110_map_generation(const F110Sim* sim);
 
 /* Per-kernel timing for bench.py's roofline: when enabled every f110_step records CUDA events around its three
  * kernels on the launch stream (not capturable into a CUDA graph while enabled).  f110_get_kernel_timing

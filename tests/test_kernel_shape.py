@@ -2,7 +2,8 @@
 
 DESIGN.md section 3 rests on properties of the generated code that a harmless-looking source change can lose without any
 test failing: the hot loop of the ray-march must contain no call (5 % of the kernel) and no local-memory
-traffic, and the kernel must fit the 40 registers that keep 12 CTAs of 128 threads resident per SM."""
+traffic and stay short (it is the dependent chain of every lookup), and the kernel must fit the 40 registers that keep 12
+CTAs of 128 threads resident per SM (32 for the 16-CTA variant)."""
 import re
 import shutil
 import subprocess
@@ -33,18 +34,18 @@ def _lidar_variants(fns):
 
 def test_lidar_kernel_register_budget():
     fns = _lidar_variants(_functions(["-res-usage"]))
-    assert len(fns) == 8                                        # COUNT x IDENT x DIRECT
+    assert len(fns) == 20                                       # fraction bits {generic, 19..22} x COUNT x DIRECT
     for name, lines in fns.items():
         text = " ".join(lines)
         reg = int(re.search(r"REG:(\d+)", text).group(1))
         local = int(re.search(r"LOCAL:(\d+)", text).group(1))
         assert reg <= 40, (name, reg)
-        assert local == 0, (name, local)                        # no spills, no stack frame
+        assert local <= 128, (name, local)                      # a few words of the per-unit bookkeeping, none in the hot loop
 
 
 def test_lidar_hot_loop_has_no_call_and_no_local_memory():
     fns = _lidar_variants(_functions(["-sass"]))
-    assert len(fns) == 8
+    assert len(fns) == 20
     for name, lines in fns.items():
         ins = []
         for line in lines:
@@ -62,4 +63,7 @@ def test_lidar_hot_loop_has_no_call_and_no_local_memory():
         hot = min(loops, key=len)                               # the guarded fixed-point march
         assert not any("CALL" in t for t in hot), name
         assert not any(("LDL" in t) or ("STL" in t) for t in hot), name
-        assert len(hot) <= 48, (name, len(hot))                 # 38 (identity map origin) to 45 (rotated origin) today
+        tuned = "lidar_kernelILi0E" not in name
+        assert len(hot) <= (24 if tuned else 34), (name, len(hot))    # 23 tuned / 30 generic today (was 38 with the world-frame march)
+        if tuned:                                                   # no kernel parameter is re-read inside the tuned loop
+            assert not any(("LDC" in t) or ("LDCU" in t) for t in hot), name
