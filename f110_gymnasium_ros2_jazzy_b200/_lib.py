@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("F110_B200_LIB") or os.path.join(_HERE, "csrc", "libf110_b200.so")   # env override: tuning builds only
 
-F110_ABI_VERSION = 1
+F110_ABI_VERSION = 2
 F110_NUM_PARAMS = 18
 F110_NUM_STATS = 8
 F110_MAX_AGENTS = 16
@@ -44,7 +44,7 @@ class F110StepIO(C.Structure):
                 ("active_mask", C.c_void_p),
                 ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("scans_f64", C.c_void_p),
                 ("scans_f32", C.c_void_p), ("state", C.c_void_p), ("collisions", C.c_void_p), ("toggles", C.c_void_p),
-                ("lap_times", C.c_void_p), ("lap_counts", C.c_void_p), ("time", C.c_void_p)]
+                ("lap_times", C.c_void_p), ("lap_counts", C.c_void_p), ("time", C.c_void_p), ("agent_poses", C.c_void_p)]
 
 
 class F110RewardConfig(C.Structure):

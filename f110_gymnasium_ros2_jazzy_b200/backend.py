@@ -29,6 +29,7 @@ _OUT_SPECS = {
     'lap_times': (lambda N, A, B: (N, A), torch.float64),
     'lap_counts': (lambda N, A, B: (N, A), torch.float64),
     'time': (lambda N, A, B: (N,), torch.float64),
+    'agent_poses': (lambda N, A, B: (N, A, 3), torch.float64),
 }
 ALL_OUTPUTS = tuple(_OUT_SPECS)
 FAST_OUTPUTS = ('obs', 'reward', 'terminated')
@@ -236,7 +237,7 @@ class BatchSim(object):
 
     # merge order of f110_step_host_async (include/f110_b200.h)
     _IN_ORDER = ('actions', 'reset_poses', 'noise', 'reset_mask')
-    _OUT_ORDER = ('scans_f64', 'state', 'lap_times', 'lap_counts', 'time', 'obs', 'scans_f32', 'reward', 'toggles',
+    _OUT_ORDER = ('scans_f64', 'state', 'agent_poses', 'lap_times', 'lap_counts', 'time', 'obs', 'scans_f32', 'reward', 'toggles',
                   'terminated', 'collisions')
 
     def host_blocks(self, outputs=ALL_OUTPUTS, actions_dtype=np.float32, noise=True):

@@ -515,13 +515,13 @@ int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     if (!sim->io_blob) {
         // room for the device mirror of every field of F110StepIO at once, allocated on first use
         sim->io_bytes = NA * 2 * 8 + NA * B * 8 + N + NA * 3 * 8 + N                       // inputs
-                      + N * (B + 8) * 4 + N * 4 + N + NA * B * 8 + NA * B * 4 + NA * 7 * 8  // outputs
+                      + N * (B + 8) * 4 + N * 4 + N + NA * B * 8 + NA * B * 4 + NA * 7 * 8 + NA * 3 * 8  // outputs
                       + NA + NA * 4 + NA * 8 + NA * 8 + N * 8 + 4096;
         CUDA_TRY(cudaMalloc(&sim->io_blob, sim->io_bytes));
     }
     cudaStream_t s = sim->host_stream;
     F110StepIO d = *hio;
-    Xfer in[5], out[11];
+    Xfer in[5], out[12];
     int n_in = 0, n_out = 0;
     char* cur = sim->io_blob;
     // field present in the caller's struct -> next slot of io_blob; the device-side struct points there
@@ -542,6 +542,7 @@ int f110_step_host_async(F110Sim* sim, const F110StepIO* hio) {
     // between two of them.  (With only obs / reward / terminated requested, obs sits at the 256-byte aligned start.)
     SLOT(out, n_out, scans_f64, NA * B * sizeof(double))
     SLOT(out, n_out, state, NA * 7 * sizeof(double))
+    SLOT(out, n_out, agent_poses, NA * 3 * sizeof(double))
     SLOT(out, n_out, lap_times, NA * sizeof(double))
     SLOT(out, n_out, lap_counts, NA * sizeof(double))
     SLOT(out, n_out, time, N * sizeof(double))

@@ -1079,6 +1079,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
 #pragma unroll
             for (int k = 0; k < 7; ++k) o[k] = st.x[k][s];   // this thread wrote the zeroed entries itself in stage A
         }
+        if (io.agent_poses) { double* o = io.agent_poses + (size_t)s * 3; o[0] = e.pre[a][0]; o[1] = e.pre[a][1]; o[2] = e.pre[a][2]; }
     }
 
     // ---- stage D: opponent ray-cast (ray_cast_agents :206-227).  The lidar kernel already wrote every scan; only the
@@ -1200,6 +1201,7 @@ __global__ void __launch_bounds__(128) post_single_kernel(SimConst c, SimState s
 #pragma unroll
         for (int k = 0; k < 7; ++k) o[k] = st.x[k][s];
     }
+    if (io.agent_poses) { double* o = io.agent_poses + (size_t)s * 3; o[0] = px; o[1] = py; o[2] = sc.pre_yaw[s]; }
     if (io.time) io.time[env] = new_time;
     if (io.reward) io.reward[env] = (float)c.timestep;
     if (io.terminated) io.terminated[env] = done ? 1 : 0;

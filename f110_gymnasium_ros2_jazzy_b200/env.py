@@ -11,7 +11,8 @@ Documented extensions:
     (the reference raises IndexError in _pack_flat_obs, f110_env.py:554,566).
   * ``obs_mode='scans'`` returns the (A, B) f32 scans instead of the flat vector, the shape
     jazzy_bridge/gym_bridge.py:113-114,265-267 indexes.
-  * ``map`` may be given without ``map_dir`` as a path without extension (gym_bridge.py:77-80 style).
+  * ``map`` may be given without ``map_dir`` as a path without extension (gym_bridge.py:77-80); that call selects
+    ``obs_mode='scans'`` by default, which is what the bridge's ``list(obs[0])`` / ``list(obs[1])`` need.
   * ``noise`` selects the lidar-noise source, see simulator.Simulator.
   * ``edt='device'`` builds the distance transform with the exact EDT kernel instead of scipy (same bits; update_map
     in milliseconds).
@@ -47,7 +48,11 @@ class F110Env(gym.Env):
             self.map_name = kwargs['map']
             self.map_path = self.map_dir + self.map_name + '.yaml'
         elif 'map' in kwargs:
-            # extension: bare path without extension (the bridge's calling convention)
+            # The ROS bridge's calling convention (gym_bridge.py:77-80): `map` alone, a path without extension.  The bridge
+            # then indexes the observation per agent -- list(obs[0]), list(obs[1]) are the scans it publishes
+            # (:112-114, :264-267) -- so in this mode the observation is the (A, B) f32 scan array unless obs_mode says
+            # otherwise.  (With the reference's flat observation obs[0] is a scalar and the bridge cannot run.)
+            kwargs.setdefault('obs_mode', 'scans')
             base = os.path.splitext(kwargs['map'])[0]
             self.map_dir = os.path.dirname(base) + '/'
             self.map_name = os.path.basename(base)

@@ -65,9 +65,21 @@ except Exception:  # gymnasium absent
 
 
 def make(env_id, **kwargs):
-    """gym.make for 'f110-v0' / 'f110_gym:f110-v0' that works with or without gymnasium."""
-    name = env_id.split(':')[-1]
-    if name != 'f110-v0':
+    """gym.make as gymnasium resolves ``'module:id'``: import the module (which registers the id), then build the id's entry
+    point.  With gymnasium installed this IS gymnasium.make; without it the shim registry above is used, so
+    ``make('f110_gym:f110-v0', ...)`` -- the string every consumer of the reference uses -- behaves the same either way."""
+    import importlib
+    if HAVE_GYMNASIUM:
+        return gym.make(env_id, **kwargs)
+    module, _, name = env_id.rpartition(':')
+    if module:
+        importlib.import_module(module)
+    if name not in _REGISTRY:
         raise ValueError("unknown env id %r" % env_id)
-    from .env import F110Env
-    return F110Env(**kwargs)
+    entry_point, reg_kwargs = _REGISTRY[name]
+    if isinstance(entry_point, str):
+        mod, _, attr = entry_point.partition(':')
+        entry_point = getattr(importlib.import_module(mod), attr)
+    kw = dict(reg_kwargs.get('kwargs', {}))
+    kw.update(kwargs)
+    return entry_point(**kw)

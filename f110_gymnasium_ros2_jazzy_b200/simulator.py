@@ -17,6 +17,46 @@ class Integrator(Enum):   # base_classes.py:40-42
     Euler = 2
 
 
+class RaceCar(object):
+    """Read-only view of one vehicle of a Simulator, with the attributes of the reference's RaceCar that its consumers
+    and tests read (base_classes.py:45-158): ``state`` fp64[7] = [x, y, steer, v, yaw, yaw_rate, slip], ``params``,
+    ``in_collision`` (iTTC), ``is_ego``, ``time_step``, ``num_beams``, ``fov``, ``ttc_thresh``, ``steer_buffer_size``.
+    The vehicle itself lives on the device; ``state`` is the host copy of the last step's output."""
+    ttc_thresh = 0.005          # base_classes.py:115
+    steer_buffer_size = 2       # base_classes.py:109
+
+    def __init__(self, sim, index):
+        self._sim, self._index = sim, index
+
+    @property
+    def state(self):
+        return self._sim._state[self._index].copy()
+
+    @property
+    def params(self):
+        return self._sim._agent_params[self._index]
+
+    @property
+    def in_collision(self):
+        return bool(self._sim._ttc_collisions[self._index])
+
+    @property
+    def is_ego(self):
+        return self._index == self._sim.ego_idx
+
+    @property
+    def time_step(self):
+        return self._sim.time_step
+
+    @property
+    def num_beams(self):
+        return self._sim.num_beams
+
+    @property
+    def fov(self):
+        return self._sim.fov
+
+
 class Simulator(object):
     """Drop-in for f110_gym.envs.base_classes.Simulator.
 
@@ -36,6 +76,7 @@ class Simulator(object):
         self.ego_idx = ego_idx
         self.params = params
         self.num_beams = num_beams
+        self.fov = fov
         self.noise_mode = noise
         self.edt = edt    # 'host': scipy as the reference; 'device': exact EDT kernel (bit-identical map, ~25x faster)
         self.agent_poses = np.empty((self.num_agents, 3))
@@ -49,6 +90,10 @@ class Simulator(object):
         self._pending_reset = None
         self.last = None
         self._blocks = {}        # action dtype -> pinned host blocks
+        self._state = np.zeros((self.num_agents, 7))
+        self._ttc_collisions = np.zeros(self.num_agents, bool)
+        self._agent_params = [dict(params) for _ in range(self.num_agents)]
+        self.agents = [RaceCar(self, i) for i in range(self.num_agents)]   # base_classes.py:504-510
 
     def set_map(self, map_path, map_ext):
         self.backend.set_map(map_path, map_ext, edt=self.edt)
@@ -57,6 +102,9 @@ class Simulator(object):
         if agent_idx >= self.num_agents:
             raise IndexError('Index given is out of bounds for list of agents.')
         self.backend.update_params(params, agent_idx)
+        for i in range(self.num_agents):
+            if agent_idx < 0 or i == agent_idx:
+                self._agent_params[i] = dict(params)
 
     def reset(self, poses):
         poses = np.asarray(poses, dtype=np.float64)
@@ -65,6 +113,10 @@ class Simulator(object):
         self.backend.sim_reset(poses[None])
         torch.cuda.current_stream(self.backend.device).synchronize()   # the host-buffer step runs on the library's own stream
         self._rngs = [np.random.default_rng(seed=self.seed) for _ in range(self.num_agents)]
+        self._state = np.zeros((self.num_agents, 7))
+        self._state[:, 0:2] = poses[:, 0:2]
+        self._state[:, 4] = poses[:, 2]
+        self._ttc_collisions = np.zeros(self.num_agents, bool)
 
     def _fill_noise(self, dst):
         """dst [1, A, B]: one normal(0, 0.01) draw per car from its own generator (laser_models.py:450-452)."""
@@ -104,7 +156,11 @@ class Simulator(object):
 
     def _observations(self, o):
         st = o['state'][0]
-        self.agent_poses = st[:, [0, 1, 4]].copy()
+        # recorded before check_ttc zeroes a colliding car's yaw (base_classes.py:587 vs :248-250)
+        self.agent_poses = o['agent_poses'][0].copy()
+        self._state = st
+        # RaceCar.in_collision is the iTTC flag alone; an iTTC hit zeroes state[3:] (base_classes.py:246-252), GJK does not
+        self._ttc_collisions = (o['collisions'][0] != 0) & np.all(st[:, 3:] == 0, axis=1)
         self.collisions = o['collisions'][0].astype(np.float64)
         observations = {'ego_idx': self.ego_idx,
                         'scans': [o['scans_f64'][0, i].copy() for i in range(self.num_agents)],

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define F110_ABI_VERSION 1
+#define F110_ABI_VERSION 2
 
 /* vehicle parameter vector, order of the keys of the params dict (f110_env.py:132-156) */
 #define F110_NUM_PARAMS 18
@@ -125,6 +125,8 @@ typedef struct F110StepIO {
     double* lap_times;           /* [N][A] */
     double* lap_counts;          /* [N][A] */
     double* time;                /* [N]       current_time (f110_env.py:406) */
+    double* agent_poses;         /* [N][A][3] Simulator.agent_poses: x, y, yaw after the dynamics update and BEFORE the iTTC
+                                    zeroing of a colliding car's yaw (base_classes.py:587 vs :248-250) */
 } F110StepIO;
 
 const char* f110_last_error(void);

@@ -33,7 +33,7 @@ class IO(C.Structure):       # struct F110StepIO
     _fields_ = [("actions", C.c_void_p), ("actions_f64", C.c_int32), ("host_flags", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("noise", "reset_mask", "reset_poses", "active_mask", "obs", "reward", "terminated",
                                           "scans_f64", "scans_f32", "state", "collisions", "toggles", "lap_times",
-                                          "lap_counts", "time")]
+                                          "lap_counts", "time", "agent_poses")]
 
 
 def _p(a):
@@ -74,7 +74,7 @@ class Simulator(object):
         self.time_step = time_step
         self.agent_poses = np.empty((num_agents, 3))
         self.collisions = np.zeros((num_agents,))
-        cfg = Cfg(1, 0, 1, num_agents, NUM_BEAMS, THETA_DIS, getattr(integrator, "value", integrator or 1), ego_idx, 0, 0,
+        cfg = Cfg(L.f110_abi_version(), 0, 1, num_agents, NUM_BEAMS, THETA_DIS, getattr(integrator, "value", integrator or 1), ego_idx, 0, 0,
                   FOV, 1e-4, 30.0, time_step, lidar_dist, 0.005, params.get("lidar_max", 30.0), 0.0, seed)
         self.h = C.c_void_p()
         _check(L.f110_create(C.byref(cfg), _p(np.array([params[k] for k in KEYS], np.float64)), C.byref(self.h)))
@@ -110,10 +110,11 @@ class Simulator(object):
         A = self.num_agents
         act = np.ascontiguousarray(control_inputs, np.float64)
         noise = np.stack([r.normal(0., 0.01, size=NUM_BEAMS) for r in self.rngs])   # the reference's stream, injected
-        st, sc, col = np.empty((A, 7)), np.empty((A, NUM_BEAMS)), np.empty(A, np.uint8)
-        io = IO(actions=_p(act), actions_f64=1, noise=_p(noise), state=_p(st), scans_f64=_p(sc), collisions=_p(col))
+        st, sc, col, ap = np.empty((A, 7)), np.empty((A, NUM_BEAMS)), np.empty(A, np.uint8), np.empty((A, 3))
+        io = IO(actions=_p(act), actions_f64=1, noise=_p(noise), state=_p(st), scans_f64=_p(sc), collisions=_p(col),
+                agent_poses=_p(ap))
         _check(L.f110_step_host(self.h, C.byref(io)))
-        self.agent_poses = st[:, [0, 1, 4]].copy()
+        self.agent_poses = ap                                    # recorded before check_ttc (:587 vs :248-250)
         self.collisions = col.astype(np.float64)
         return {'ego_idx': self.ego_idx, 'scans': list(sc), 'poses_x': list(st[:, 0]), 'poses_y': list(st[:, 1]),
                 'poses_theta': list(st[:, 4]), 'linear_vels_x': list(st[:, 3]), 'linear_vels_y': [0.] * A,

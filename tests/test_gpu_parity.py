@@ -924,28 +924,96 @@ def test_device_edt_bit_identical_to_scipy():
     sim.close()
 
 
-def test_ros_bridge_call_pattern(tmp_path):
-    """jazzy_bridge/.../gym_bridge.py:77-80,112-114,226-228,264-280: make(map=<path without extension>, map_ext, num_agents),
-    reset(options=...), step(float64 (A, 2)), then obs[0] / obs[1] as per-agent scans and info['poses_*'][i].  The reference's
-    own env returns a flat vector there (so the bridge cannot index it); obs_mode='scans' is the documented shim."""
+def test_ros_bridge_call_sequence_as_written(tmp_path):
+    """The literal call sequence of jazzy_bridge/.../gym_bridge.py, nothing added: gym.make('f110_gym:f110-v0', map=<path
+    without extension>, map_ext=..., num_agents=...) (:77-80), reset(options=np.array([[sx, sy, stheta], [sx1, sy1, stheta1]]))
+    followed by list(obs[0]) / list(obs[1]) (:112-114), step(np.array([[steer, speed], [steer, speed]])) in float64 (:224-229),
+    _update_sim_state's reads of obs[i] and info['poses_x' | 'poses_y' | 'poses_theta' | 'linear_vels_x' | 'linear_vels_y' |
+    'ang_vels_z'][i] (:264-280), and the pose-reset callbacks (:197-210).  'f110_gym' resolves through the alias package at
+    the repository root exactly as gymnasium resolves a 'module:id' string; the scans layout is selected by the bridge's own
+    calling convention (map= without map_dir=)."""
     _torch()
-    import f110_gymnasium_ros2_jazzy_b200 as f
+    from f110_gymnasium_ros2_jazzy_b200 import gym_compat as gym        # gymnasium itself when it is installed
     map_dir, name = H.write_map_files('open_square', str(tmp_path))
-    env = f.make('f110_gym:f110-v0', map=map_dir + name, map_ext='.png', num_agents=2, obs_mode='scans')
-    obs, info = env.reset(options=np.array([[0.0, 0.0, 0.0], [2.0, 0.5, 0.0]]))
-    ego_scan, opp_scan = list(obs[0]), list(obs[1])
-    assert len(ego_scan) == 1080 and len(opp_scan) == 1080
-    for _ in range(5):
-        obs, reward, terminated, truncated, info = env.step(np.array([[0.1, 1.0], [0.0, 1.5]]))   # float64, as the bridge sends
-    assert obs.shape == (2, 1080) and obs.dtype == np.float32
-    assert float(info['poses_x'][1]) > 2.0 and abs(float(info['linear_vels_y'][0])) == 0.0
-    assert np.isfinite(info['ang_vels_z']).all() and info['poses_theta'].shape == (2,)
-    # single-agent form (gym_bridge.py:124,226)
-    env1 = f.make('f110_gym:f110-v0', map=map_dir + name, map_ext='.png', num_agents=1, obs_mode='scans')
-    obs, info = env1.reset(options=np.array([[0.0, 0.0, 0.0]]))
-    obs, reward, terminated, truncated, info = env1.step(np.array([[0.0, 1.0]]))
-    assert len(list(obs[0])) == 1080
-    env.close(); env1.close()
+    map_path = map_dir + name
+    sx, sy, stheta, sx1, sy1, stheta1 = 0.0, 0.0, 0.0, 2.0, 0.5, 0.0
+    # ---- two agents (:77-80, :100-114)
+    env = gym.make('f110_gym:f110-v0', map=map_path, map_ext='.png', num_agents=2)
+    obs, info = env.reset(options=np.array([[sx, sy, stheta], [sx1, sy1, stheta1]]))
+    ego_scan = list(obs[0]); opp_scan = list(obs[1])
+    assert len(ego_scan) == 1080 and len(opp_scan) == 1080 and isinstance(ego_scan[0], np.floating)
+    ego_pose, ego_speed, opp_pose, opp_speed = [sx, sy, stheta], [0.0, 0.0, 0.0], [sx1, sy1, stheta1], [0.0, 0.0, 0.0]
+    ego_steer, ego_requested_speed, opp_steer, opp_requested_speed = 0.3, 1.0, 0.0, 1.5
+    for _ in range(20):
+        obs, reward, terminated, truncated, info = env.step(np.array([[ego_steer, ego_requested_speed], [opp_steer, opp_requested_speed]]))
+        ego_scan = list(obs[0])
+        opp_scan = list(obs[1])
+        opp_pose[0] = info['poses_x'][1]; opp_pose[1] = info['poses_y'][1]; opp_pose[2] = info['poses_theta'][1]
+        opp_speed[0] = info['linear_vels_x'][1]; opp_speed[1] = info['linear_vels_y'][1]; opp_speed[2] = info['ang_vels_z'][1]
+        ego_pose[0] = info['poses_x'][0]; ego_pose[1] = info['poses_y'][0]; ego_pose[2] = info['poses_theta'][0]
+        ego_speed[0] = info['linear_vels_x'][0]; ego_speed[1] = info['linear_vels_y'][0]; ego_speed[2] = info['ang_vels_z'][0]
+    assert reward == env.unwrapped.timestep and truncated is False and terminated in (True, False)
+    assert opp_pose[0] > sx1 and ego_pose[2] > 0.0 and ego_speed[1] == 0.0 and np.isfinite(ego_speed + opp_speed).all()
+    assert len(ego_scan) == 1080 and max(ego_scan) <= 30.05
+    # pose reset from rviz (:197, :210)
+    rx, ry, rtheta = -1.0, 1.0, 0.5
+    obs, info = env.reset(options=np.array([[rx, ry, rtheta], opp_pose]))
+    assert abs(info['poses_x'][0] - rx) < 1e-6 and len(list(obs[1])) == 1080
+    obs, info = env.reset(options=np.array([list(ego_pose), [rx, ry, rtheta]]))
+    assert abs(info['poses_y'][1] - ry) < 1e-6
+    env.close()
+    # ---- one agent (:124-125, :226)
+    env = gym.make('f110_gym:f110-v0', map=map_path, map_ext='.png', num_agents=1)
+    obs, info = env.reset(options=np.array([[sx, sy, stheta]]))
+    ego_scan = list(obs[0])
+    obs, reward, terminated, truncated, info = env.step(np.array([[ego_steer, ego_requested_speed]]))
+    assert len(list(obs[0])) == 1080 and info['poses_x'].shape == (1,)
+    env.close()
+
+
+def test_train_ddpg_loop_shape(tmp_path):
+    """rl_training/train_ddpg.py:58-65 and :150-202 with the env swapped in and nothing else changed in the calls: gym.make(
+    'f110_gym:f110-v0', render_mode=..., map_dir=..., map=..., map_ext=..., num_agents=2), reset(options=float32 start poses),
+    then per step the opponent's action from info["scans"][1], np.stack([ego, opp]).astype(float32), env.step(actions) ->
+    (next_obs, _, terminated, truncated, info), the shaped reward on next_obs, done = terminated or truncated.  The opponent
+    is the reference's gap-follow controller (oracle restatement, pinned on tests/golden/gap_follow.npz); the whole rollout is
+    compared with the oracle stepping the same actions."""
+    _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import gym_compat as gym
+    from oracle.f110_oracle import Oracle, gap_follow_action as gap_follow
+    map_dir, name = H.write_map_files('Shanghai_map', str(tmp_path))
+    env = gym.make('f110_gym:f110-v0', render_mode='human_fast', map_dir=map_dir, map=name, map_ext='.png', num_agents=2)
+    assert env.unwrapped.timestep == 0.01
+    start_poses = [[0.0, 0.0, 0.0], [3.0, 0.5, 0.0]]                         # ddpg_config.yaml:11-12
+    orc = Oracle(1, 2); orc.set_map_arrays(*H.golden_map('Shanghai_map'))
+    s, c, a, bc, sd = H.tables(); orc.set_tables(s, c); orc.set_beam_tables(a, bc, sd)
+    rng = np.random.default_rng(0)
+    nz = np.random.default_rng(42)                                          # the env's lidar noise stream (seed 42, re-seeded on reset)
+    obs, info = env.reset(options=np.array(start_poses, dtype=np.float32))
+    noise = nz.normal(0., 0.01, size=1080)
+    ref = orc.reset(np.array(start_poses, dtype=np.float32).astype(np.float64)[None], np.broadcast_to(noise, (1, 2, 1080)))
+    assert obs.shape == (1088,) and obs.dtype == np.float32
+    assert np.abs(obs - ref['obs'][0]).max() <= 1e-6
+    steps, done = 0, False
+    action_low, action_high = np.array([-0.4189, 0.0], np.float32), np.array([0.4189, 6.0], np.float32)
+    for step in range(120):
+        ego_action = rng.uniform(low=action_low, high=action_high).astype(np.float32)
+        opp_action = gap_follow(info["scans"][1]).astype(np.float32)
+        actions = np.stack([ego_action, opp_action], axis=0).astype(np.float32)
+        next_obs, _, terminated, truncated, info = env.step(actions)
+        noise = nz.normal(0., 0.01, size=1080)
+        ref = orc.step(actions[None], np.broadcast_to(noise, (1, 2, 1080)))
+        assert bool(terminated) == bool(ref['terminated'][0]) and truncated is False
+        assert np.array_equal(info['collisions'], ref['collisions'][0].astype(np.int8))
+        assert np.abs(next_obs - ref['obs'][0]).max() <= 1e-6
+        assert (np.abs(info['scans'][1] - ref['scans'][0, 1].astype(np.float32)) <= 1e-5).mean() >= SCAN_FRAC
+        done = bool(terminated or truncated)
+        obs = next_obs
+        steps += 1
+        if done:
+            break
+    assert steps >= 20
+    env.close()
 
 
 @pytest.mark.parametrize("num_envs,num_agents,num_beams,fov", [(5, 16, 1080, 4.7), (33, 6, 64, 3.0), (7, 4, 4320, 4.7), (1, 2, 32, 1.0)])

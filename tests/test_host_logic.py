@@ -213,3 +213,26 @@ def test_device_replay_buffer_ring_and_per_formulas():
         small.sample()
     small.add(*batch(2, 1))
     assert small.sample()[0].shape == (4,)                    # fewer than a batch stored: with replacement
+
+
+def test_f110_gym_alias_resolves_like_gymnasium():
+    """gym.make('f110_gym:f110-v0', ...) -- the id string of train_ddpg.py:58 and gym_bridge.py:77 -- imports a module called
+    f110_gym and looks the id up afterwards (f110_gymnasium/gym/f110_gym/__init__.py:1-5).  The alias package at the repository
+    root must register the id with an entry point that is the B200 F110Env, and f110_gym.envs must export the classes the
+    reference's does."""
+    import importlib
+    import f110_gym
+    import f110_gym.envs as envs
+    from f110_gymnasium_ros2_jazzy_b200 import F110Env, Integrator, Simulator, gym_compat
+    assert envs.F110Env is F110Env and envs.Simulator is Simulator and envs.Integrator is Integrator
+    assert hasattr(envs, 'RaceCar')
+    if gym_compat.HAVE_GYMNASIUM:
+        import gymnasium
+        spec = gymnasium.spec('f110-v0')
+        entry = spec.entry_point
+    else:
+        entry, _ = gym_compat._REGISTRY['f110-v0']
+    mod, _, attr = entry.partition(':')
+    assert getattr(importlib.import_module(mod), attr) is F110Env
+    with pytest.raises(Exception):
+        gym_compat.make('f110_gym:no-such-env-v0')
