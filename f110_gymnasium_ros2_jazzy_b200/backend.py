@@ -293,7 +293,13 @@ class BatchSim(object):
                                pin_memory=pinned) for k in keys}
 
     # ------------------------------------------------------------------ checkpoint / stats
+    @property
+    def map_generation(self):
+        """Incremented by every map change; F110VecEnv compares it to know that a captured CUDA graph is stale."""
+        return int(self.lib.f110_map_generation(self.h))
+
     def state_dict(self):
+        """The library's checkpoint blob: a versioned header (layout, N, A, B) + the whole persistent state arena."""
         n = int(self.lib.f110_state_nbytes(self.h))
         blob = torch.empty(n, dtype=torch.uint8, device=self.device)
         _lib.check(self.lib.f110_get_state(self.h, _ptr(blob), self._stream()))

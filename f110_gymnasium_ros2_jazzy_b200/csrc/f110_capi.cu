@@ -79,6 +79,7 @@ struct F110Sim {
     unsigned long long redone_rays = 0;   // rays the lidar kernel redid in exact arithmetic, refreshed likewise
     int lidar_blocks = 0;         // CTAs of one resident wave of the lidar kernel (persistent warps)
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
+    uint64_t ckpt_header_words[8] = {0};   // host staging of the checkpoint header (see f110_get_state)
 };
 
 namespace {
@@ -182,6 +183,9 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     if (cfg->num_envs < 1 || cfg->num_agents < 1 || cfg->num_agents > F110_MAX_AGENTS || cfg->num_beams < 32 || cfg->num_beams > 32768 || cfg->theta_dis < 2)
         return fail(F110_ERR_INVALID, "need num_envs >= 1, 1 <= num_agents <= %d, 32 <= num_beams <= 32768, theta_dis >= 2", F110_MAX_AGENTS);
     if (cfg->ego_idx < 0 || cfg->ego_idx >= cfg->num_agents) return fail(F110_ERR_INDEX, "ego_idx out of range");
+    // beams further than 2 pi apart would wrap the direction table more than once and are the same directions again
+    if (!(cfg->fov > 0.0) || cfg->fov > 2.0 * F110_PI) return fail(F110_ERR_INVALID, "fov must lie in (0, 2 pi]");
+    if (!(cfg->eps >= 0.0) || !(cfg->max_range > 0.0) || !(cfg->timestep > 0.0)) return fail(F110_ERR_INVALID, "need eps >= 0, max_range > 0, timestep > 0");
     if (cfg->integrator != F110_INTEGRATOR_RK4 && cfg->integrator != F110_INTEGRATOR_EULER)
         return fail(F110_ERR_INTEGRATOR, "Invalid Integrator Specified. Please choose RK4 or Euler");
     if ((double)cfg->num_envs * cfg->num_agents * cfg->num_beams >= 2147483648.0)
@@ -587,19 +591,56 @@ int f110_step_host(F110Sim* sim, const F110StepIO* hio) {
     return f110_host_sync(sim);
 }
 
-int64_t f110_state_nbytes(const F110Sim* sim) { return sim ? (int64_t)sim->state_bytes : 0; }
+// A checkpoint is a 64-byte header followed by the state arena.  The header names the layout, so that a blob from another
+// build or another batch shape is refused instead of being copied over the arena.
+namespace {
+struct CheckpointHeader {
+    uint32_t magic;      // 'F110'
+    uint32_t layout;     // bumped whenever layout_state changes
+    int32_t N, A, B;
+    uint32_t reserved;
+    uint64_t state_bytes;
+    uint64_t pad[4];
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header is 64 bytes");
+constexpr uint32_t CKPT_MAGIC = 0x30313146u, CKPT_LAYOUT = 2u;
+CheckpointHeader checkpoint_header(const F110Sim* sim) {
+    CheckpointHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = CKPT_MAGIC; h.layout = CKPT_LAYOUT;
+    h.N = sim->c.N; h.A = sim->c.A; h.B = sim->c.B;
+    h.state_bytes = sim->state_bytes;
+    return h;
+}
+}  // namespace
+
+int64_t f110_state_nbytes(const F110Sim* sim) { return sim ? (int64_t)(sizeof(CheckpointHeader) + sim->state_bytes) : 0; }
 
 int f110_get_state(F110Sim* sim, void* dst, void* stream) {
     if (!sim || !dst) return fail(F110_ERR_INVALID, "null argument");
     Guard g(sim->cfg.device);
-    CUDA_TRY(cudaMemcpyAsync(dst, sim->state_blob, sim->state_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    const CheckpointHeader hd = checkpoint_header(sim);
+    memcpy(sim->ckpt_header_words, &hd, sizeof(hd));   // staged in the handle: the asynchronous copy reads it later
+    CUDA_TRY(cudaMemcpyAsync(dst, sim->ckpt_header_words, sizeof(CheckpointHeader), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst) + sizeof(CheckpointHeader), sim->state_blob, sim->state_bytes,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return F110_OK;
 }
 
 int f110_set_state(F110Sim* sim, const void* src, void* stream) {
     if (!sim || !src) return fail(F110_ERR_INVALID, "null argument");
     Guard g(sim->cfg.device);
-    CUDA_TRY(cudaMemcpyAsync(sim->state_blob, src, sim->state_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CheckpointHeader h;
+    CUDA_TRY(cudaMemcpyAsync(&h, src, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    const CheckpointHeader want = checkpoint_header(sim);
+    if (h.magic != want.magic) return fail(F110_ERR_INVALID, "not an f110 checkpoint (bad magic)");
+    if (h.layout != want.layout) return fail(F110_ERR_INVALID, "checkpoint layout %u, this library reads layout %u", h.layout, want.layout);
+    if (h.N != want.N || h.A != want.A || h.B != want.B || h.state_bytes != want.state_bytes)
+        return fail(F110_ERR_INVALID, "checkpoint is for %d envs x %d agents x %d beams, this handle has %d x %d x %d", h.N, h.A, h.B,
+                    want.N, want.A, want.B);
+    CUDA_TRY(cudaMemcpyAsync(sim->state_blob, static_cast<const char*>(src) + sizeof(CheckpointHeader), sim->state_bytes,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return F110_OK;
 }
 

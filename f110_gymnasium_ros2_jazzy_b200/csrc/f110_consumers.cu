@@ -142,7 +142,18 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
     if (!scans || !actions || num_scans < 0 || num_beams < 1 || num_beams > 8192 || window_size < 1 || window_size > 15)
         return f110_set_error(F110_ERR_INVALID, "f110_gap_follow: need non-null buffers, 1 <= num_beams <= 8192, 1 <= window_size <= 15");
     if (num_scans == 0) return F110_OK;
-    gap_follow_kernel<<<(unsigned)num_scans, GF_THREADS, 2 * sizeof(float) * num_beams, (cudaStream_t)stream>>>(
+    const size_t gf_smem = 2 * sizeof(float) * (size_t)num_beams;
+    if (gf_smem > 48 * 1024) {   // above the default 48 KB a kernel has to opt in to its dynamic shared memory
+        static bool opted_in = false;
+        if (!opted_in) {
+            if (cudaFuncSetAttribute(gap_follow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) {
+                cudaGetLastError();
+                return f110_set_error(F110_ERR_CUDA, "f110_gap_follow: cannot reserve 64 KB of shared memory");
+            }
+            opted_in = true;
+        }
+    }
+    gap_follow_kernel<<<(unsigned)num_scans, GF_THREADS, gf_smem, (cudaStream_t)stream>>>(
         scans, scan_stride, num_beams, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
         bubble_radius, threshold);
     return cudaPeekAtLastError() == cudaSuccess ? F110_OK : f110_set_error(F110_ERR_CUDA, "f110_gap_follow: kernel launch failed");

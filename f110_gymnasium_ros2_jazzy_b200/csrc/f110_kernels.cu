@@ -1015,9 +1015,10 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
         // cone -> beam-index intervals (supersets by one beam each side), clipped to the reference window
         int f0 = e.lo[u], f1 = e.hi[u], b0 = B, b1 = -1;
         const double alpha = asin(R / dist) + 1e-6;
-        if (dist > R * (1.0 + 1e-6) && alpha < 0.75) {
-            // beam angles lie inside (-pi + 0.75, pi - 0.75) (fov <= 4.7 rad): a cone of half-width < 0.75 around a
-            // bearing in [-pi, pi] can only meet them un-wrapped
+        // beam angles lie inside [-fov/2, fov/2]: a cone of half-width < pi - fov/2 around a bearing in [-pi, pi] can only
+        // meet them un-wrapped (0.79 rad at the default 4.7 rad lidar; a lidar of 2 (pi - 0.05) rad or more is never pruned)
+        const double cone_max = fmin(0.75, F110_PI - 0.5 * c.fov - 0.01);
+        if (dist > R * (1.0 + 1e-6) && alpha < cone_max) {
             double phi = atan2(dy, dx) - e.pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
             if (phi > F110_PI) phi -= 2 * F110_PI;
             else if (phi < -F110_PI) phi += 2 * F110_PI;

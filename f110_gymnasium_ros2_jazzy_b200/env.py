@@ -188,6 +188,25 @@ class F110Env(gym.Env):
         for render_callback in F110Env.render_callbacks:
             render_callback(F110Env.renderer)
 
+    def state_dict(self):
+        """Checkpoint of the env: the library's versioned state blob, the host generators of the reference's lidar-noise
+        stream (noise='numpy') and the lap bookkeeping this class mirrors on the host."""
+        rng = None if self.sim._rngs is None else [r.bit_generator.state for r in self.sim._rngs]
+        return {'backend': self.sim.backend.state_dict(), 'noise_rng': rng, 'current_time': self.current_time,
+                'lap_times': self.lap_times.copy(), 'lap_counts': self.lap_counts.copy(), 'toggle_list': self.toggle_list.copy(),
+                'start': (np.array(self.start_xs), np.array(self.start_ys), np.array(self.start_thetas), self.start_rot.copy())}
+
+    def load_state_dict(self, sd):
+        self.sim.backend.load_state_dict(sd['backend'])
+        torch.cuda.current_stream(self.sim.backend.device).synchronize()
+        if sd['noise_rng'] is not None:
+            self.sim._rngs = [np.random.default_rng() for _ in sd['noise_rng']]
+            for r, st in zip(self.sim._rngs, sd['noise_rng']):
+                r.bit_generator.state = st
+        self.current_time = sd['current_time']
+        self.lap_times, self.lap_counts, self.toggle_list = sd['lap_times'].copy(), sd['lap_counts'].copy(), sd['toggle_list'].copy()
+        self.start_xs, self.start_ys, self.start_thetas, self.start_rot = sd['start']
+
     def close(self):
         if getattr(self, 'sim', None) is not None:
             self.sim.backend.close()
@@ -227,6 +246,7 @@ class F110VecEnv(object):
         self._graph = None
         self._act = torch.zeros((num_envs, num_agents, 2), dtype=torch.float32, device=self.device)
         self._steps_eager = 0
+        self._map_generation = self.backend.map_generation
 
     def reset(self, poses, noise=None):
         """poses [N, A, 3] (or [A, 3], broadcast to every env)."""
@@ -241,6 +261,8 @@ class F110VecEnv(object):
 
     def step(self, actions, noise=None):
         o = self.backend.out
+        if self._graph is not None and self._map_generation != self.backend.map_generation:
+            self._drop_graph()      # the map was changed behind the env's back (backend.set_map*): see set_map
         if self.cuda_graph and noise is None and self.auto_reset and self.start_poses is not None:
             self._act.copy_(torch.as_tensor(actions, device=self.device).reshape(self._act.shape))
             if self._graph is None and self._steps_eager >= 1:
@@ -265,6 +287,34 @@ class F110VecEnv(object):
         else:
             o = self.backend.step(actions, noise)
         return o['obs'], o['reward'], o['terminated'], self.truncated, o
+
+    def set_map(self, map_path, map_ext, edt='host'):
+        """update_map for the whole batch.  The step kernels receive the map descriptor by value, so a captured CUDA graph
+        still holds the previous (freed) map: it is dropped here and re-captured by the next steps."""
+        self.backend.set_map(map_path, map_ext, edt=edt)
+        self._drop_graph()
+
+    def set_map_arrays(self, dt, resolution, origin):
+        self.backend.set_map_arrays(dt, resolution, origin)
+        self._drop_graph()
+
+    def _drop_graph(self):
+        self._graph = None
+        self._steps_eager = 0
+        self._map_generation = self.backend.map_generation
+
+    def state_dict(self):
+        """Everything needed to continue the batch bit for bit in another process: the library's state blob (versioned,
+        BatchSim.state_dict), plus what lives on this side of the C ABI -- the terminated flags (the next step's reset mask
+        under auto-reset) and the start poses."""
+        return {'backend': self.backend.state_dict(), 'terminated': self.backend.out['terminated'].clone(),
+                'start_poses': None if self.start_poses is None else self.start_poses.clone(), 'auto_reset': self.auto_reset}
+
+    def load_state_dict(self, sd):
+        self.backend.load_state_dict(sd['backend'])
+        self.backend.out['terminated'].copy_(sd['terminated'].to(self.device))
+        self.start_poses = None if sd['start_poses'] is None else sd['start_poses'].to(self.device).contiguous()
+        self._drop_graph()          # a captured step holds the old start-pose tensor
 
     def close(self):
         self.backend.close()

@@ -61,7 +61,8 @@ class DeviceRollout(object):
     """ego = policy(obs), opponent = gap-follow on its own scan, env.step -- no host round trip per step.
 
     ``reward_fn`` (optional, e.g. ShapedReward) replaces the env's constant reward, as train_ddpg.py:179 does.
-    ``replay`` (optional, e.g. DeviceReplayBuffer) receives every transition (obs, ego action, reward, next obs, done).
+    ``replay`` (optional, e.g. DeviceReplayBuffer) receives every transition (obs, ego action, reward, next obs, done)
+    except the auto-reset steps (see step).
     ``env`` is an F110VecEnv with num_agents == 2 and 'scans_f32' among its outputs; ``policy`` maps the observation
     tensor [N, B+8] to ego actions [N, 2] (e.g. Actor).  ``opponent`` may be 'gap_follow' or a constant (steer, speed).
     """
@@ -85,25 +86,38 @@ class DeviceRollout(object):
 
     def reset(self, poses):
         self.obs, o = self.env.reset(poses)
-        self._fresh = torch.ones(self.env.num_envs, dtype=torch.uint8, device=self.env.device)
+        n, dev = self.env.num_envs, self.env.device
+        # envs whose NEXT step is the first real step of an episode: every env, right after a reset
+        self._first = torch.ones(n, dtype=torch.uint8, device=dev)
+        self._resetting = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._fresh = torch.zeros(n, dtype=torch.uint8, device=dev)
         return self.obs
 
     @torch.no_grad()
     def step(self):
+        """One step of the loop train_ddpg.py:160-202 runs per env.  An env that terminated on the previous step is auto-reset
+        by this one: that step is the reference's ``env.reset()`` between episodes (:152), not a transition -- its action is
+        ignored by the env, its observation is the reset observation.  Such envs are kept out of the replay memory (the
+        reference ``break``s on done and never stores a terminal -> reset pair), get reward 0, and their reward object starts
+        over (``reward_fn.reset()``, :151) so that its first call is on the first real next_obs, as in the reference."""
         self.actions[:, 0, :] = self.policy(self.obs)
         if self.opponent == 'gap_follow':
             gap_follow_actions(self.env.backend.out['scans_f32'], self.actions, agent_idx=1)
-        if self.reward_fn is not None:
-            # an env that terminated on the previous step is auto-reset by this one: its reward object starts over too
-            self._fresh.copy_(self.env.backend.out['terminated'])
+        self._resetting.copy_(self.env.backend.out['terminated'])      # this step resets these envs (auto-reset)
+        if self.env.backend.out['terminated'].data_ptr() == self._resetting.data_ptr():
+            raise RuntimeError("internal: the terminated flags must be copied before the step rewrites them")
         if self.replay is not None:
             self._prev_obs.copy_(self.obs)          # the env rewrites its observation tensor in place
         self.obs, reward, terminated, truncated, info = self.env.step(self.actions)
         if self.reward_fn is not None:
+            # reward object restarted on the reset step itself (its value there is discarded) and again on the first real step
+            torch.maximum(self._resetting, self._first, out=self._fresh)
             reward = self.reward_fn(self.obs, self._fresh)
+            reward.masked_fill_(self._resetting.bool(), 0.0)
         self.reward = reward
         if self.replay is not None:
-            self.replay.add(self._prev_obs, self.actions[:, 0, :], reward, self.obs, terminated)
+            self.replay.add(self._prev_obs, self.actions[:, 0, :], reward, self.obs, terminated, keep=self._resetting == 0)
+        self._first.copy_(self._resetting)          # the step after a reset step is an episode's first real step
         return self.obs, reward, terminated, truncated, info
 
 
@@ -124,41 +138,64 @@ class DeviceReplayBuffer(object):
         self.capacity, self.batch_size, self.alpha, self.eps = int(capacity), int(batch_size), float(alpha), float(priority_epsilon)
         dev = torch.device(device) if device is not None else torch.device('cuda' if torch.cuda.is_available() else 'cpu')
         self.device = dev
-        self.obs = torch.zeros((capacity, obs_dim), dtype=torch.float32, device=dev)
-        self.next_obs = torch.zeros((capacity, obs_dim), dtype=torch.float32, device=dev)
-        self.action = torch.zeros((capacity, act_dim), dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(capacity, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(capacity, dtype=torch.uint8, device=dev)
-        self.priority = torch.zeros(capacity, dtype=torch.float32, device=dev)
-        self.length, self.next_idx = 0, 0
+        # one row more than the capacity: transitions masked out of an add() are written there, so that a masked add needs
+        # neither a compaction nor a host round trip
+        self._obs = torch.zeros((capacity + 1, obs_dim), dtype=torch.float32, device=dev)
+        self._next_obs = torch.zeros((capacity + 1, obs_dim), dtype=torch.float32, device=dev)
+        self._action = torch.zeros((capacity + 1, act_dim), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros(capacity + 1, dtype=torch.float32, device=dev)
+        self._done = torch.zeros(capacity + 1, dtype=torch.uint8, device=dev)
+        self._priority = torch.zeros(capacity + 1, dtype=torch.float32, device=dev)
+        self.obs, self.next_obs, self.action = self._obs[:capacity], self._next_obs[:capacity], self._action[:capacity]
+        self.reward, self.done, self.priority = self._reward[:capacity], self._done[:capacity], self._priority[:capacity]
+        self._len = torch.zeros((), dtype=torch.int64, device=dev)      # ring-buffer counters live on the device
+        self._next = torch.zeros((), dtype=torch.int64, device=dev)
         self._max_prio = torch.ones((), dtype=torch.float32, device=dev)     # running maximum, kept on the device
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
+
+    @property
+    def length(self):
+        return int(self._len)        # (synchronises)
+
+    @property
+    def next_idx(self):
+        return int(self._next)
 
     def __len__(self):
         return self.length
 
     @torch.no_grad()
-    def add(self, obs, action, reward, next_obs, done, priority=None):
-        """One transition per env: obs/next_obs [n, obs_dim], action [n, act_dim], reward [n], done [n]."""
+    def add(self, obs, action, reward, next_obs, done, priority=None, keep=None):
+        """One transition per env: obs/next_obs [n, obs_dim], action [n, act_dim], reward [n], done [n].
+        ``keep`` [n] (optional): only the rows where it is non-zero are stored, in order, without a host round trip."""
         n = obs.shape[0]
         if n > self.capacity:
             raise ValueError("more transitions in one add() than the buffer holds")
-        idx = (self.next_idx + torch.arange(n, device=self.device)) % self.capacity
+        empty = self._len == 0
         if priority is None:
-            p0 = self._max_prio.expand(n) if self.length > 0 else torch.ones(n, dtype=torch.float32, device=self.device)
+            p0 = torch.where(empty, torch.ones_like(self._max_prio), self._max_prio).expand(n)
         else:
             p0 = torch.as_tensor(priority, dtype=torch.float32, device=self.device).expand(n)
         p0 = torch.clamp(p0, 1e-8, torch.finfo(torch.float32).max)
-        self.obs.index_copy_(0, idx, obs.to(torch.float32))
-        self.next_obs.index_copy_(0, idx, next_obs.to(torch.float32))
-        self.action.index_copy_(0, idx, action.to(torch.float32))
-        self.reward.index_copy_(0, idx, reward.to(torch.float32).reshape(n))
-        self.done.index_copy_(0, idx, done.to(torch.uint8).reshape(n))
-        self.priority.index_copy_(0, idx, p0)
-        self._max_prio = torch.maximum(self._max_prio, p0.max()) if self.length > 0 else p0.max()
-        self.length = min(self.length + n, self.capacity)
-        self.next_idx = (self.next_idx + n) % self.capacity
+        if keep is None:
+            count = torch.full((), n, dtype=torch.int64, device=self.device)
+            idx = (self._next + torch.arange(n, device=self.device)) % self.capacity
+        else:
+            k = keep.to(device=self.device).reshape(n) != 0
+            rank = torch.cumsum(k, 0)
+            count = rank[-1]
+            idx = torch.where(k, (self._next + rank - 1) % self.capacity, torch.full_like(rank, self.capacity))
+        self._obs.index_copy_(0, idx, obs.to(torch.float32))
+        self._next_obs.index_copy_(0, idx, next_obs.to(torch.float32))
+        self._action.index_copy_(0, idx, action.to(torch.float32))
+        self._reward.index_copy_(0, idx, reward.to(torch.float32).reshape(n))
+        self._done.index_copy_(0, idx, done.to(torch.uint8).reshape(n))
+        self._priority.index_copy_(0, idx, p0)
+        new_max = torch.where(empty, p0.max(), torch.maximum(self._max_prio, p0.max()))
+        self._max_prio = torch.where(count > 0, new_max, self._max_prio)
+        self._len = torch.clamp(self._len + count, max=self.capacity)
+        self._next = (self._next + count) % self.capacity
 
     def probabilities(self):
         ps = (self.priority[:self.length] + self.eps).double() ** self.alpha     # the sum is formed in float32, as numpy does (:88)

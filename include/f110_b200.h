@@ -178,7 +178,11 @@ int f110_host_sync(F110Sim* sim);
  * for a caller that shards its envs over several handles. */
 int f110_step_host_multi(F110Sim* const* sims, const F110StepIO* ios, int32_t count);
 
-/* Checkpoint of the whole persistent simulation state as one opaque blob (DEVICE pointer). */
+/* Checkpoint of the whole persistent simulation state as one opaque blob (DEVICE pointer): a 64-byte header (magic, layout
+ * version, N, A, B, size) followed by the state arena.  f110_set_state reads the header back (it synchronises the stream)
+ * and refuses a blob of another layout version or batch shape with F110_ERR_INVALID.  What the blob does NOT hold is the
+ * caller's: the terminated flags it uses as the next reset mask, its start poses, host-side noise generators --
+ * F110VecEnv.state_dict / F110Env.state_dict add those. */
 int64_t f110_state_nbytes(const F110Sim* sim);
 int f110_get_state(F110Sim* sim, void* dst, void* stream);
 int f110_set_state(F110Sim* sim, const void* src, void* stream);

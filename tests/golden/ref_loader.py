@@ -67,16 +67,21 @@ def load_reference():
     if REF_GYM not in sys.path:
         sys.path.insert(0, REF_GYM)
     # the real renderer subclasses pyglet.window.Window (rendering.py:58); never used on the step path
+    if not getattr(sys.modules.get("f110_gym"), "_is_reference", False):
+        # the repository's own f110_gym alias package (module id of gym.make) may be loaded: the reference's goes in its place
+        for name in [k for k in sys.modules if k == "f110_gym" or k.startswith("f110_gym.")]:
+            del sys.modules[name]
     if "f110_gym.envs.rendering" not in sys.modules:
         import importlib.machinery
         pkg = types.ModuleType("f110_gym")
         pkg.__path__ = [os.path.join(REF_GYM, "f110_gym")]
+        pkg._is_reference = True
         sub = types.ModuleType("f110_gym.envs")
         sub.__path__ = [os.path.join(REF_GYM, "f110_gym", "envs")]
         rend = types.ModuleType("f110_gym.envs.rendering")
         rend.EnvRenderer = object
-        sys.modules.setdefault("f110_gym", pkg)
-        sys.modules.setdefault("f110_gym.envs", sub)
+        sys.modules["f110_gym"] = pkg
+        sys.modules["f110_gym.envs"] = sub
         sys.modules["f110_gym.envs.rendering"] = rend
     ns = types.SimpleNamespace()
     from f110_gym.envs import dynamic_models, laser_models, collision_models, base_classes, f110_env

@@ -446,9 +446,10 @@ def test_known_answer_dynamics_on_device():
     p['lidar_max'] = 30.0
     dt = 1e-3
     be = GpuBackend(1, 1, 'open_square', params=p, integrator=2, timestep=dt)
-    # inject the state through the checkpoint blob: x[k] are the first seven 256-byte-aligned arrays (NA = 1)
+    # inject the state through the checkpoint blob: after the 64-byte header, x[k] are the first seven 256-byte-aligned
+    # arrays of the arena (NA = 1)
     blob = be.sim.state_dict()['blob'].clone()
-    blob.view(torch.float64)[0:7 * 32:32] = torch.tensor(x_st, dtype=torch.float64, device=blob.device)
+    blob.view(torch.float64)[8:8 + 7 * 32:32] = torch.tensor(x_st, dtype=torch.float64, device=blob.device)
     be.sim.load_state_dict({'blob': blob, 'N': 1, 'A': 1, 'B': 1080})
     out = be.step(np.array([[[0.5, 30.0]]], np.float64), np.zeros((1, 1, 1080)))
     # pid(): the steering FIFO is still empty -> steer = 0 -> sv = -sv_max; speed error -> accl clipped to +a_max
@@ -719,6 +720,14 @@ def test_gap_follow_kernel_bit_exact():
     assert np.array_equal(a[:N, 1], g['actions'].astype(np.float32))
     ref = np.stack([gap_follow_action(s) for s in more]).astype(np.float32)
     assert np.array_equal(a[N:, 1], ref)
+    # 8000 beams: 64 KB of dynamic shared memory, above the 48 KB a kernel gets without opting in
+    wide = np.random.default_rng(9).uniform(0.3, 8.0, size=(3, 8000)).astype(np.float32)
+    tw = torch.from_numpy(np.stack([wide, wide], axis=1).copy()).cuda()
+    actw = torch.zeros((3, 2, 2), dtype=torch.float32, device='cuda')
+    gap_follow_actions(tw, actw, agent_idx=1, angle_increment=np.pi / 8000)
+    torch.cuda.synchronize()
+    refw = np.stack([gap_follow_action(s, angle_increment=np.pi / 8000) for s in wide]).astype(np.float32)
+    assert np.array_equal(actw.cpu().numpy()[:, 1], refw)
 
 
 def test_consumers_survive_non_finite_inputs():
@@ -790,36 +799,131 @@ def test_device_rollout_runs_without_host_sync():
 def test_device_rollout_fills_device_replay_buffer():
     """DeviceRollout(replay=DeviceReplayBuffer): every transition lands in the device buffer in env order --
     (obs before the step, the ego action that was applied, reward, obs after, done) -- and a prioritised batch can be
-    drawn, all without a host copy (train_ddpg.py:160-188's remember / replay shape)."""
+    drawn, all without a host copy (train_ddpg.py:160-188's remember / replay shape).  The step that auto-resets an env
+    which terminated on the previous step is the reference's env.reset() between episodes (:152), not a transition: it
+    must not reach the buffer (the reference breaks on done, :197), its reward is 0, and the shaped reward restarts so
+    that its first value of the new episode is computed on the first real next_obs."""
     torch = _torch()
-    from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceReplayBuffer, DeviceRollout, F110VecEnv
-    N, T = 32, 12
+    from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceReplayBuffer, DeviceRollout, F110VecEnv, ShapedReward
+    N, T = 32, 60
     m = H.golden_map('Shanghai_map')
     cl = H.load('maps')['Shanghai_map__centerline_poses']
     idx = np.linspace(0, len(cl) - 1, N).round().astype(int)
     poses = np.stack([cl[idx], cl[(idx + 40) % len(cl)]], axis=1)
     env = F110VecEnv(N, num_agents=2, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'scans_f32'))
-    torch.manual_seed(1)
-    actor = Actor(1088, 2, [-0.4189, 0.0], [0.4189, 20.0]).cuda()
+
+    class FullLock(torch.nn.Module):                  # steers into the wall at speed: episodes end within the rollout
+        def forward(self, obs):
+            return torch.tensor([0.4189, 9.0], device=obs.device).expand(obs.shape[0], 2)
+    g = H.load('reward')
+    rfn = ShapedReward(N, g['centerline'])
+    solo = ShapedReward(N, g['centerline'])           # the same reward objects driven by hand, reset exactly at episode starts
     buf = DeviceReplayBuffer(capacity=N * T, batch_size=64, device='cuda')
-    ro = DeviceRollout(env, actor, replay=buf)
+    ro = DeviceRollout(env, FullLock(), reward_fn=rfn, replay=buf)
     obs0 = ro.reset(poses).clone()
-    seen = []
+    want, resetting_prev, first = [], torch.zeros(N, dtype=torch.bool, device='cuda'), torch.ones(N, dtype=torch.bool, device='cuda')
+    n_reset_steps = 0
     for t in range(T):
         before = ro.obs.clone()
+        resetting = env.backend.out['terminated'].clone().bool()          # envs this step auto-resets
         obs, r, term, trunc, info = ro.step()
-        seen.append((before, ro.actions[:, 0].clone(), r.clone(), obs.clone(), term.clone()))
+        # hand-driven reference: no call at all on a reset step; restart flag on the first real step of an episode
+        expect = solo(obs.clone(), (first | resetting).to(torch.uint8)).clone()   # (value on reset steps is discarded, as in the rollout)
+        real = ~resetting
+        assert torch.all(r[resetting] == 0)
+        assert torch.equal(r[real], expect[real])
+        n_reset_steps += int(resetting.sum())
+        for e in torch.nonzero(real).flatten().tolist():
+            want.append((before[e].clone(), ro.actions[e, 0].clone(), r[e].clone(), obs[e].clone(), term[e].clone()))
+        first = resetting
     torch.cuda.synchronize()
-    assert len(buf) == N * T and buf.next_idx == 0 and buf.obs.is_cuda
-    for t, (o, a, r, no, d) in enumerate(seen):
-        sl = slice(t * N, (t + 1) * N)
-        assert torch.equal(buf.obs[sl], o) and torch.equal(buf.next_obs[sl], no) and torch.equal(buf.action[sl], a)
-        assert torch.equal(buf.reward[sl], r) and torch.equal(buf.done[sl], d)
+    assert n_reset_steps > 0, "the scenario must contain terminations"
+    assert len(buf) == N * T - n_reset_steps == len(want) and buf.obs.is_cuda
+    for k, (o, a, r, no, d) in enumerate(want):
+        assert torch.equal(buf.obs[k], o) and torch.equal(buf.next_obs[k], no) and torch.equal(buf.action[k], a)
+        assert float(buf.reward[k]) == float(r.float()) and int(buf.done[k]) == int(d)
     assert torch.equal(buf.obs[:N], obs0)
     idxs, (o, a, r, no, d), w = buf.sample(beta=0.4)
     assert o.shape == (64, 1088) and w.is_cuda and float(w.max()) == 1.0 and len(set(idxs.tolist())) == 64
     buf.update_priorities(idxs, torch.rand(64, device='cuda') + 0.1)
+    # a second reset() of the rollout restarts every reward object on the next step
+    ro.reset(poses)
+    ro.step()
+    assert bool(torch.all(ro._fresh == 1))
     env.close()
+
+
+def test_checkpoint_is_versioned_and_env_level_resume_is_exact():
+    """f110_get_state / f110_set_state carry a header (magic, layout version, N, A, B): a blob of another shape or a corrupted
+    one is refused.  F110VecEnv.state_dict adds what lives above the C ABI (terminated flags = next reset mask, start
+    poses): a fresh env loaded from it continues bit for bit, including the auto-reset of envs that had just terminated."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import F110VecEnv
+    N = 64
+    m = H.golden_map('Shanghai_map')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
+    kw = dict(num_agents=1, map_arrays=m, outputs=('obs', 'reward', 'terminated', 'state'), noise_std=0.01, seed=7)
+    env = F110VecEnv(N, **kw)
+    env.reset(poses)
+    g = torch.Generator(device='cuda'); g.manual_seed(3)
+    acts = torch.rand((80, N, 1, 2), generator=g, device='cuda') * torch.tensor([0.8378, 12.0], device='cuda') + torch.tensor([-0.4189, 2.0], device='cuda')
+    for k in range(40):
+        env.step(acts[k])
+    assert int(env.backend.out['terminated'].sum()) >= 0
+    sd = env.state_dict()
+    ref = []
+    for k in range(40, 80):
+        o, r, t, _, info = env.step(acts[k])
+        ref.append((o.clone(), t.clone(), info['state'].clone()))
+    # a second env, as another process would build it
+    env2 = F110VecEnv(N, **kw)
+    env2.reset(poses[::-1].copy())            # different history before the load
+    env2.load_state_dict(sd)
+    for k in range(40, 80):
+        o, r, t, _, info = env2.step(acts[k])
+        assert torch.equal(o, ref[k - 40][0]) and torch.equal(t, ref[k - 40][1]) and torch.equal(info['state'], ref[k - 40][2]), k
+    # the blob is refused by a handle of another shape, and when its header is damaged
+    env3 = F110VecEnv(N // 2, **kw)
+    with pytest.raises(Exception):
+        env3.backend.load_state_dict(dict(sd['backend'], N=N // 2))
+    bad = dict(sd['backend'], blob=sd['backend']['blob'].clone())
+    bad['blob'][0] ^= 0xFF
+    with pytest.raises(Exception):
+        env2.backend.load_state_dict(bad)
+    for e in (env, env2, env3):
+        e.close()
+
+
+def test_cuda_graph_is_dropped_when_the_map_changes():
+    """The step kernels take the map descriptor by value: a graph captured before set_map would replay with the freed map.
+    F110VecEnv re-captures (also when the map is changed on the backend directly)."""
+    torch = _torch()
+    from f110_gymnasium_ros2_jazzy_b200 import F110VecEnv
+    N = 32
+    m1 = H.golden_map('Shanghai_map')
+    dt2, res2, o2 = H.golden_map('open_square')
+    cl = H.load('maps')['Shanghai_map__centerline_poses']
+    poses = np.zeros((N, 1, 3)); poses[:, 0, 0] = np.linspace(-3, 3, N)
+    kw = dict(num_agents=1, outputs=('obs', 'reward', 'terminated', 'scans_f64'), noise_std=0.0)
+    envs = [F110VecEnv(N, map_arrays=m1, cuda_graph=cg, **kw) for cg in (True, False)]
+    act = torch.zeros((N, 1, 2), device='cuda'); act[..., 1] = 1.0
+    for e in envs:
+        e.reset(cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :])
+        for _ in range(4):
+            e.step(act)
+    assert envs[0]._graph is not None
+    envs[0].backend.set_map_arrays(dt2, res2, o2)        # behind the env's back
+    envs[1].set_map_arrays(dt2, res2, o2)
+    for e in envs:
+        e.reset(poses)
+        for _ in range(4):
+            e.step(act)
+    torch.cuda.synchronize()
+    assert envs[0]._graph is not None
+    assert torch.equal(envs[0].backend.out['scans_f64'], envs[1].backend.out['scans_f64'])
+    for e in envs:
+        e.close()
 
 
 def test_c4_full_size_sharded_properties():
@@ -1016,7 +1120,8 @@ def test_train_ddpg_loop_shape(tmp_path):
     env.close()
 
 
-@pytest.mark.parametrize("num_envs,num_agents,num_beams,fov", [(5, 16, 1080, 4.7), (33, 6, 64, 3.0), (7, 4, 4320, 4.7), (1, 2, 32, 1.0)])
+@pytest.mark.parametrize("num_envs,num_agents,num_beams,fov", [(5, 16, 1080, 4.7), (33, 6, 64, 3.0), (7, 4, 4320, 4.7), (1, 2, 32, 1.0),
+                                                              (6, 3, 720, 6.2)])   # 355-degree lidar: no cone pruning in K3, beams wrap the table
 def test_shape_extremes_vs_oracle(num_envs, num_agents, num_beams, fov):
     """Edges of the supported shapes: the maximum agent count (one env per post-kernel CTA), the minimum beam count, a
     non-default field of view, 4320 beams, ragged env counts -- each against the oracle with injected noise."""

@@ -221,8 +221,11 @@ def test_f110_gym_alias_resolves_like_gymnasium():
     root must register the id with an entry point that is the B200 F110Env, and f110_gym.envs must export the classes the
     reference's does."""
     import importlib
+    for name in [k for k in sys.modules if k == "f110_gym" or k.startswith("f110_gym.")]:
+        del sys.modules[name]                      # (the differential tests load the REFERENCE's package under this name)
     import f110_gym
     import f110_gym.envs as envs
+    assert f110_gym.__file__.startswith(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from f110_gymnasium_ros2_jazzy_b200 import F110Env, Integrator, Simulator, gym_compat
     assert envs.F110Env is F110Env and envs.Simulator is Simulator and envs.Integrator is Integrator
     assert hasattr(envs, 'RaceCar')
@@ -236,3 +239,5 @@ def test_f110_gym_alias_resolves_like_gymnasium():
     assert getattr(importlib.import_module(mod), attr) is F110Env
     with pytest.raises(Exception):
         gym_compat.make('f110_gym:no-such-env-v0')
+    for name in [k for k in sys.modules if k == "f110_gym" or k.startswith("f110_gym.")]:
+        del sys.modules[name]
