@@ -4,6 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--agents A] [--beams B]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...      # the CPU arm: oracle port on all host cores
+  python bench.py --config c4|c5 ...        # BASELINE configs 4 / 5 (not the driver's line, which is C3)
 
 Workload (config C3 of BASELINE.json / SURVEY 8d): E = 4096 single-agent envs per GPU on the Shanghai map
 (2000x2000 cells, 0.06505 m), 1080-beam 270-degree lidar, RK4 single-track dynamics, start poses spread over
@@ -37,7 +38,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (C3: 4096)")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 (default, the metric's configuration): 4096 single-agent envs per GPU.  c4: 262 144 envs in total, sharded "
+                         "over the GPUs (combine with --beams 270..4320 and --map-upsample 2|4 for the sweep).  c5: 65 536 two-agent envs "
+                         "in total driven by DeviceRollout (actor 1088-128-128-2 + gap-follow opponent, observations consumed on the device)")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 4096 for c3, 262144 / N for c4, 65536 / N for c5)")
     ap.add_argument("--agents", type=int, default=1)
     ap.add_argument("--beams", type=int, default=1080)
     ap.add_argument("--map", default="Shanghai_map")
@@ -50,31 +55,23 @@ def parse():
                     "(a small first chunk starts the downloads sooner)")
     ap.add_argument("--pipe-chunks", type=int, default=4, help="env chunks of the e2e send/recv (cross-step pipelined) figure")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.config == "c5":
+        a.agents = 2
+    if a.envs <= 0:
+        a.envs = {"c3": 4096, "c4": 262144 // world, "c5": 65536 // world}[a.config]
+    return a
 
 
 def load_workload(args, num_envs, env_offset=0, total_envs=None):
-    """Map + start poses from the committed fixtures (nothing reads /root/reference at run time)."""
-    from tests import helpers as H
-    dt, res, origin = H.golden_map(args.map)
-    if args.map_upsample > 1:
-        # C4 "large maps": nearest-neighbour upsampling of the occupancy, resolution divided accordingly
-        from scipy.ndimage import distance_transform_edt
-        k = args.map_upsample
-        free = np.kron(dt > 0, np.ones((k, k), bool))
-        res = res / k
-        dt = res * distance_transform_edt(np.where(free, 255., 0.))
-    total = total_envs or num_envs
-    if args.map == "Shanghai_map":
-        cl = H.load('maps')['Shanghai_map__centerline_poses']
-        idx = np.linspace(0, len(cl) - 1, total).round().astype(int)[env_offset:env_offset + num_envs]
-        poses = np.zeros((num_envs, args.agents, 3))
-        for a in range(args.agents):
-            poses[:, a] = cl[(idx + 25 * a) % len(cl)]
-    else:
-        poses = np.zeros((num_envs, args.agents, 3))
-        poses[:, :, 0] = 1.0 * np.arange(args.agents)[None]
-    return (dt, res, origin), poses
+    """Map + start poses from the arrays the package ships (nothing reads /root/reference or tests/ at run time)."""
+    from f110_gymnasium_ros2_jazzy_b200 import workloads
+    if args.map != "Shanghai_map":
+        raise SystemExit("bench.py ships the Shanghai map only (--map-upsample 2|4 gives BASELINE C4's large maps)")
+    map_arrays = workloads.shanghai_map(args.map_upsample)
+    poses = workloads.start_poses(num_envs, args.agents, env_offset, total_envs or num_envs)
+    return map_arrays, poses
 
 
 def action_stream(torch, steps, n, a, device, seed=1234):
@@ -203,8 +200,12 @@ def reference_main(args):
 
 
 def workload_config(args, envs_per_gpu, note=None):
-    c = {"workload": "C3: %d single-agent f110-v0 envs per GPU, %s, RK4 ST dynamics, %d-beam 4.7 rad lidar, uniform random "
-                     "actions, auto-reset on done" % (envs_per_gpu, args.map, args.beams),
+    names = {"c3": "C3", "c4": "C4", "c5": "C5"}
+    what = ("%d single-agent f110-v0 envs per GPU" % envs_per_gpu) if args.agents == 1 else \
+           ("%d %d-agent f110-v0 envs per GPU" % (envs_per_gpu, args.agents))
+    extra = ", DeviceRollout: actor 1088-128-128-2 + gap-follow opponent on the device" if args.config == "c5" else ""
+    c = {"workload": "%s: %s, %s%s, RK4 ST dynamics, %d-beam 4.7 rad lidar, uniform random actions, auto-reset on done%s"
+                     % (names[args.config], what, args.map, "" if args.map_upsample == 1 else " x%d" % args.map_upsample, args.beams, extra),
          "envs_per_gpu": envs_per_gpu, "agents": args.agents, "beams": args.beams, "map": args.map,
          "map_upsample": args.map_upsample, "parallelism": "env-index sharding, no step-path collective"}
     if note:
@@ -219,6 +220,40 @@ def emit(line):
 
 
 _JSON_OUT = sys.stdout
+
+
+def numba_reference():
+    """The baseline north_star names -- the unmodified numba reference under a one-process-per-core lock-step vector runner --
+    as measured in the BUILD CONTAINER by tools/numba_reference_baseline.py (numba and /root/reference do not exist on the
+    GPU box).  Reported beside the in-run C-port figure, labelled as what it is."""
+    p = os.path.join(ROOT, "profiles", "numba_reference.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    r = next((x for x in d["results"] if x["shape"] == "sim1" and x["workers"] > 1), None)
+    if r is None:
+        return None
+    return {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": r["workers"], "per_core": r["env_steps_per_s_per_core"],
+            "where": d["where"], "runner": d["runner"], "shape": "Simulator.step, 1 agent (the C3 shape), scan + pose returned",
+            "source": "profiles/numba_reference.json (tools/numba_reference_baseline.py)"}
+
+
+def fabric_probe(torch, dist, dev, world, nbytes, iters=40):
+    """Bare device->host copy of one step's download (same bytes, pinned destination), every rank at once, no kernels: the
+    ceiling of the e2e figure on this box.  -> GB/s of this rank (max over nothing: the caller gathers)."""
+    d = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    h = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
+    for _ in range(5):
+        h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    return iters * nbytes / (time.perf_counter() - t0) / 1e9
 
 
 def main():
@@ -255,15 +290,23 @@ def main():
     total_envs = E * world
     lo, hi = shard_range(total_envs, rank, world)
     map_arrays, poses = load_workload(args, hi - lo, lo, total_envs)
+    rollout = args.config == "c5"
+    outputs = ('obs', 'reward', 'terminated', 'scans_f32') if rollout else ('obs', 'reward', 'terminated')
 
     def make_env(count=False):
         env = F110VecEnv(E, num_agents=A, num_beams=B, seed=42 + rank, device=local, auto_reset=True,
-                         outputs=('obs', 'reward', 'terminated'), noise_std=0.01, count_lookups=count, map_arrays=map_arrays)
+                         outputs=outputs, noise_std=0.01, count_lookups=count, map_arrays=map_arrays)
         env.reset(poses)
         return env
 
     env = make_env()
-    acts = action_stream(torch, W + K, E, A, dev, seed=1234 + rank)
+    acts = None if rollout else action_stream(torch, W + K, E, A, dev, seed=1234 + rank)
+    ro = None
+    if rollout:
+        from f110_gymnasium_ros2_jazzy_b200 import Actor, DeviceRollout
+        torch.manual_seed(42)
+        ro = DeviceRollout(env, Actor(B + 8, 2, [S_MIN, V_MIN], [S_MAX, V_MAX]).to(dev))
+        ro.reset(poses)
     flush = None if args.no_flush else torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -273,7 +316,10 @@ def main():
                 flush_buf.fill_(k & 0xFF)          # evict L2 (252 MiB written) before every timed step
             if per_step_events is not None:
                 per_step_events[k - first][0].record(stream)
-            env.step(acts[k])
+            if ro is not None:
+                ro.step()
+            else:
+                env.step(acts[k])
             if per_step_events is not None:
                 per_step_events[k - first][1].record(stream)
 
@@ -301,19 +347,33 @@ def main():
         dev_ms = float(t.item())
     stats = EpisodeStats().reduce(env.backend.stats())   # the path's only collective, off the step path
 
-    # ---- e2e on every rank: host buffers in and out through f110_step_host_async/f110_host_sync
+    # ---- e2e on every rank: host buffers in and out through f110_step_host_async/f110_host_sync, and beside it the bare
+    # device->host copy of the same bytes on every rank at once (what the box's host fabric gives, no kernels)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not rollout:
         el, el_pipe = e2e_run(args, map_arrays, poses, acts, W, K, E, A, B, local, torch)
+        d2h_bytes = E * (B + 8) * 4 + E * 4 + E
+        fab = torch.tensor([fabric_probe(torch, dist, dev, world, d2h_bytes)], dtype=torch.float64, device=dev)
+        fab_all = [float(fab)]
         if world > 1:
             dist.barrier()
             t = torch.tensor([el, el_pipe], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el, el_pipe = float(t[0].item()), float(t[1].item())
+            g = [torch.zeros_like(fab) for _ in range(world)]
+            dist.all_gather(g, fab)
+            fab_all = [float(x) for x in g]
+        floor_ms = 1e3 * d2h_bytes / (min(fab_all) * 1e9)
         e2e = {"value": total_envs * K / el, "unit": "env-steps/s", "h2d_bytes_per_step": E * A * 2 * 4 + E + E * A * 3 * 8,
-               "d2h_bytes_per_step": E * (B + 8) * 4 + E * 4 + E, "ms_per_step": 1e3 * el / K, "n_gpus": world,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * el / K, "n_gpus": world,
                "api": "F110HostVecEnv.step -> f110_step_host_async + f110_host_sync (C ABI, pinned host buffers, env chunks %s)" % args.host_chunks,
                "bytes_are": "per GPU",
+               "fabric": {"what": "bare cudaMemcpyAsync device->host of d2h_bytes_per_step into pinned memory, all %d ranks at once, no kernels" % world,
+                          "d2h_gbs_per_rank": [round(x, 1) for x in fab_all], "d2h_gbs_aggregate": round(sum(fab_all), 1),
+                          "download_floor_ms_per_step": floor_ms, "value_ceiling": total_envs / (floor_ms * 1e-3),
+                          "frac_of_ceiling": (total_envs * K / el) / (total_envs / (floor_ms * 1e-3)),
+                          "note": "the slowest rank's bare copy bounds a synchronous step from below; see profiles/r02_d2h_fabric.json "
+                                  "for the 1 vs 8 rank figures (54.7 -> 12.0 GB/s per rank on this pool's boxes)"},
                "pipelined": {"value": total_envs * K / el_pipe, "ms_per_step": 1e3 * el_pipe / K,
                              "chunks": args.pipe_chunks,
                              "api": "F110HostVecEnv.send/recv per chunk (same copies per step; chunks out of phase across "
@@ -322,65 +382,84 @@ def main():
     value = total_envs * K / (dev_ms * 1e-3)
     rays_per_s = value * A * B
 
-    line = None
-    if rank == 0:
-        # ---- roofline of the dominant kernel (lidar ray-march): kernel-only time via the library's event pairs
-        from f110_gymnasium_ros2_jazzy_b200 import _lib
-        lidar_ms, kern_ms = kernel_breakdown(env, acts, W, min(K, 50), flush, torch)
-        cenv = make_env(count=True)
-        for k in range(W + min(K, 50)):
-            cenv.step(acts[k])
-        looks, rays = cenv.backend.lookup_count()
-        max_lookups = cenv.backend.max_lookups
-        redone_rays = cenv.backend.redone_rays
-        cenv.close()
-        lbar = looks / max(rays, 1)
-        bytes_per_ray = 8.0 * lbar + 8.0                      # L-bar fp64 cells + fp64 range out
-        alg_bytes = bytes_per_ray * E * A * B                 # per launch
-        peaks = {}
-        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk_path):
-            peaks = json.load(open(pk_path))
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / (lidar_ms * 1e-3) / 1e9
-        gather = gather_roofline(map_arrays[0], E * A * B, lbar, torch, dev)
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": load_traffic(), "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
-                    "kernel_share_of_step": lidar_ms / max(sum(kern_ms), 1e-9), "lookups_per_ray": lbar, "longest_ray_lookups": max_lookups,
-                    "rays_redone_exactly": redone_rays, "rays_counted": rays,
-                    "bytes_per_ray": bytes_per_ray,
-                    "sector_level": {"bytes_per_ray": 32.0 * lbar + 8.0, "gbs": (32.0 * lbar + 8.0) * E * A * B / (lidar_ms * 1e-3) / 1e9,
-                                     "note": "32-byte sector per gather instead of the 8 useful bytes (SURVEY 8d)"},
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                    "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]},
-                    "gather_roofline": dict(gather, frac_of_whole_map=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["whole_map_gbs"],
-                                            frac_of_touched_window=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["touched_window_gbs"])}
-        # ---- CPU arm beside it
-        cpu = None
-        if not args.no_cpu_baseline:
-            probe = cpu_arm(args, 5, 2)
-            steps = args.cpu_steps or int(min(400, max(20, 2.0 / (probe['seconds'] / 5))))   # ~2 s wall on all threads
-            c = cpu_arm(args, steps, 3)
-            cpu = {"value": c['value'], "unit": "env-steps/s", "cores": c['threads'], "kind": "port",
-                   "sample": "%d envs x %d steps of the same workload, oracle/f110_oracle.c on %d threads (%.1f s)"
-                             % (c['envs'], c['steps'], c['threads'], c['seconds'])}
-        line = {
-            "metric": "env-steps/s (1080-beam lidar)", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "rays_per_s": rays_per_s,
-            "config": dict(workload_config(args, E), total_envs=total_envs,
-                           l2="flushed between timed steps (252 MiB fill, outside the per-step events)" if flush is not None
-                           else "not flushed; per-step working set %.0f MiB" % ((E * A * B * 12 + map_arrays[0].nbytes) / 2**20),
-                           timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
-                           wall_ms_per_step_incl_flush=1e3 * t_wall / K),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "episode_stats": {k: stats[k] for k in ('episodes', 'ego_collisions', 'mean_episode_steps')},
-        }
+    # ---- everything below runs on rank 0 ALONE: the other ranks leave now instead of spinning in a barrier (an NCCL barrier
+    # is a busy wait that took host cores from the CPU arm and put a 100 % "busy" GPU beside an idle rank 0 in round 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
-        emit(line)
+    if rank != 0:
+        env.close()
+        return 0
+
+    # ---- roofline of the dominant kernel (lidar ray-march): kernel-only time via the library's event pairs
+    from f110_gymnasium_ros2_jazzy_b200 import _lib
+    if ro is not None:
+        acts = action_stream(torch, W + min(K, 50), E, A, dev, seed=1234 + rank)
+    lidar_ms, kern_ms = kernel_breakdown(env, acts, W, min(K, 50), flush, torch)
+    cenv = make_env(count=True)
+    for k in range(W + min(K, 50)):
+        cenv.step(acts[k])
+    looks, rays = cenv.backend.lookup_count()
+    max_lookups = cenv.backend.max_lookups
+    redone_rays = cenv.backend.redone_rays
+    cenv.close()
+    lbar = looks / max(rays, 1)
+    # bytes_per_ray = L-bar * s_cell + s_out, with s_cell = 8 (the reference's fp64 cell) and s_out = what this
+    # launch actually stores per ray: the f32 observation (4 B) here; + 4 / + 8 when the f32 / f64 scans are requested too.
+    s_out = 4.0 + (4.0 if 'scans_f32' in outputs else 0.0)
+    bytes_per_ray = 8.0 * lbar + s_out
+    alg_bytes = bytes_per_ray * E * A * B                 # per launch
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (lidar_ms * 1e-3) / 1e9
+    gather = gather_roofline(map_arrays[0], E * A * B, lbar, torch, dev)
+    step_ms_unevented = dev_ms / K
+    roofline = {"bound": "l2-gather",
+                "bound_note": "the cells a launch touches stay in L2 (DRAM traffic is ~1 % of the algorithmic bytes, see traffic), so the HBM "
+                              "figure below is the contract's denominator, not the limiter; gather_roofline is the same march's loads alone "
+                              "against L2, and ncu (profiles/) shows instruction issue + L2-hit latency binding the kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_traffic(), "traffic_note": "dram__bytes_read+write per lidar launch from the committed ncu capture "
+                                                           "(profiles/traffic.json), not measured in this run",
+                "kernel": "lidar_kernel", "kernel_ms": lidar_ms,
+                "kernel_share_of_step": min(1.0, lidar_ms / max(step_ms_unevented, 1e-9)),
+                "kernel_share_note": "kernel_ms (its own event pair: the events keep PDL from overlapping the neighbours) over the un-evented "
+                                     "ms_per_step; all_kernels_ms are evented too and sum to more than ms_per_step",
+                "lookups_per_ray": lbar, "longest_ray_lookups": max_lookups,
+                "rays_redone_exactly": redone_rays, "rays_counted": rays,
+                "bytes_per_ray": bytes_per_ray, "bytes_per_ray_is": "8 * lookups_per_ray + %g stored" % s_out,
+                "sector_level": {"bytes_per_ray": 32.0 * lbar + s_out, "gbs": (32.0 * lbar + s_out) * E * A * B / (lidar_ms * 1e-3) / 1e9,
+                                 "note": "32-byte sector per gather instead of the 8 useful bytes (SURVEY 8d)"},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                "all_kernels_ms": {"dynamics": kern_ms[0], "lidar": kern_ms[1], "post": kern_ms[2]},
+                "gather_roofline": dict(gather, frac_of_whole_map=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["whole_map_gbs"],
+                                        frac_of_touched_window=8.0 * lbar * E * A * B / (lidar_ms * 1e-3) / 1e9 / gather["touched_window_gbs"])}
+    # ---- CPU arm beside it (the other ranks have exited: every host core is free)
+    cpu = None
+    if not args.no_cpu_baseline:
+        probe = cpu_arm(args, 5, 2)
+        steps = args.cpu_steps or int(min(400, max(20, 2.0 / (probe['seconds'] / 5))))   # ~2 s wall on all threads
+        c = cpu_arm(args, steps, 3)
+        cpu = {"value": c['value'], "unit": "env-steps/s", "cores": c['threads'], "kind": "port",
+               "sample": "%d envs x %d steps of the same workload, oracle/f110_oracle.c on %d threads (%.1f s)"
+                         % (c['envs'], c['steps'], c['threads'], c['seconds']),
+               "numba_reference": numba_reference()}
+    line = {
+        "metric": "env-steps/s (1080-beam lidar)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if args.config == "c3" else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "rays_per_s": rays_per_s,
+        "config": dict(workload_config(args, E), total_envs=total_envs,
+                       l2="flushed between timed steps (252 MiB fill, outside the per-step events)" if flush is not None
+                       else "not flushed; per-step working set %.0f MiB" % ((E * A * B * 12 + map_arrays[0].nbytes) / 2**20),
+                       timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                       wall_ms_per_step_incl_flush=1e3 * t_wall / K),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "episode_stats": {k: stats[k] for k in ('episodes', 'ego_collisions', 'mean_episode_steps')},
+    }
+    emit(line)
     return 0
 
 

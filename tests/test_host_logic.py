@@ -241,3 +241,18 @@ def test_f110_gym_alias_resolves_like_gymnasium():
         gym_compat.make('f110_gym:no-such-env-v0')
     for name in [k for k in sys.modules if k == "f110_gym" or k.startswith("f110_gym.")]:
         del sys.modules[name]
+
+
+def test_package_workload_data_equals_the_golden_fixture():
+    """The Shanghai map and centerline the package ships for bench.py / smoke() are the arrays recorded from the reference."""
+    from f110_gymnasium_ros2_jazzy_b200 import workloads
+    g = H.load('maps')
+    free, res, origin = workloads.shanghai_free_mask()
+    shape = tuple(int(v) for v in g['Shanghai_map__shape'])
+    assert np.array_equal(np.packbits(free, axis=None), g['Shanghai_map__bits']) and free.shape == shape
+    assert res == float(g['Shanghai_map__resolution']) and origin == [float(v) for v in g['Shanghai_map__origin']]
+    assert np.array_equal(workloads.centerline_poses(), g['Shanghai_map__centerline_poses'])
+    dt, _, _ = workloads.shanghai_map()
+    assert np.array_equal(dt, H.golden_map('Shanghai_map')[0])
+    p = workloads.start_poses(16, 2, env_offset=4, total_envs=64)
+    assert p.shape == (16, 2, 3) and np.array_equal(p[0, 0], g['Shanghai_map__centerline_poses'][np.linspace(0, 6686, 64).round().astype(int)[4]])
