@@ -124,6 +124,10 @@ class BatchSim(object):
                                                float(np.cos(origin[2])), float(np.sin(origin[2]))))
         self.map_shape = m.shape
 
+    def edt_kernel_ms(self):
+        """Device time of the EDT kernels of the last set_map_image call (CUDA events)."""
+        return float(self.lib.f110_edt_kernel_ms(self.h))
+
     def get_map(self):
         dt = np.empty(self.map_shape, np.float64)
         _lib.check(self.lib.f110_get_map(self.h, dt.ctypes.data_as(C.c_void_p), dt.size))

@@ -80,6 +80,7 @@ struct F110Sim {
     int lidar_blocks = 0;         // CTAs of one resident wave of the lidar kernel (persistent warps)
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
     uint64_t ckpt_header_words[8] = {0};   // host staging of the checkpoint header (see f110_get_state)
+    EdtScratch edt;               // f110_set_map_image's device scratch, kept between calls
 };
 
 namespace {
@@ -306,6 +307,7 @@ void f110_destroy(F110Sim* sim) {
     if (sim->host_stream) { cudaStreamSynchronize(sim->host_stream); cudaStreamDestroy(sim->host_stream); }
     cudaFree(sim->state_blob); cudaFree(sim->scratch_blob); cudaFree(sim->d_tables); cudaFree(sim->d_map); cudaFree(sim->d_lidar_tables);
     cudaFree(sim->io_blob);
+    edt_scratch_free(&sim->edt);
     for (cudaEvent_t e : sim->tev) cudaEventDestroy(e);
     delete sim;
 }
@@ -395,11 +397,13 @@ int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, i
     cudaError_t e = cudaMalloc(&d, cells * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(d_mask, free_mask, cells, cudaMemcpyHostToDevice);
     int rc = -1;
-    if (e == cudaSuccess) rc = edt_device(d_mask, height, width, resolution, d, sim->host_stream);
+    if (e == cudaSuccess) rc = edt_device(d_mask, height, width, resolution, d, &sim->edt, sim->host_stream);
     cudaFree(d_mask);
     if (e != cudaSuccess || rc != 0) { cudaFree(d); cudaGetLastError(); return fail(F110_ERR_CUDA, "device EDT failed"); }
     return install_map(sim, d, height, width, resolution, orig_x, orig_y, orig_cos, orig_sin);
 }
+
+float f110_edt_kernel_ms(const F110Sim* sim) { return sim ? sim->edt.kernel_ms : -1.f; }
 
 int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells) {
     if (!sim || !dt_host) return fail(F110_ERR_INVALID, "null argument");

@@ -607,22 +607,35 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                     asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
                     decided = tx != 0u && ty != 0u;
                     if (decided) {
-                        d = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));
-                        for (;;) {
-                            X += d * dir.x;
-                            Y += d * dir.y;
-                            ux = __double2uint_rz(X);
-                            uy = __double2uint_rz(Y);
-                            const double d_next = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));
-                            total_d += d;
-                            ++nlook;
-                            if (!((TUNED ? d > 0.0 : d > eps) && total_d <= max_range)) break;
-                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));
+                        // Two lookups per trip, the roles of the two cell registers swapped between them: written as one
+                        // lookup per trip, ptxas rotates (d, d_next) through four register moves -- 4 of the loop's 23
+                        // instructions.  One exit test per lookup (ray ended OR lookup undecided; told apart after the
+                        // loop, where `still going` means undecided), one counter update per trip.
+                        double da = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb))), db = 0.0;
+                        unsigned trips = 0;
+                        bool second = false;
+#define F110_MARCH_STEP(D_CUR, D_NEXT)                                                                         \
+                            X += D_CUR * dir.x;                                                                \
+                            Y += D_CUR * dir.y;                                                                \
+                            ux = __double2uint_rz(X);                                                          \
+                            uy = __double2uint_rz(Y);                                                          \
+                            D_NEXT = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));                  \
+                            total_d += D_CUR;                                                                  \
+                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));                \
                             asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
-                            decided = tx != 0u && ty != 0u;
-                            if (!decided) break;
-                            d = d_next;
+                        for (;;) {
+                            F110_MARCH_STEP(da, db)
+                            if (!((TUNED ? da > 0.0 : da > eps) && total_d <= max_range && tx != 0u && ty != 0u)) break;
+                            F110_MARCH_STEP(db, da)
+                            if (!((TUNED ? db > 0.0 : db > eps) && total_d <= max_range && tx != 0u && ty != 0u)) { second = true; break; }
+                            ++trips;
                         }
+#undef F110_MARCH_STEP
+                        d = second ? db : da;
+                        nlook = 2u * trips + (second ? 2u : 1u);
+                        // the ray ended on this lookup (d is its last cell: a sentinel means it left the map), or it goes on
+                        // and the lookup after it could not be decided
+                        decided = !((TUNED ? d > 0.0 : d > eps) && total_d <= max_range);
                     }
                 }
                 if (live && (!decided || d < 0.0)) {
@@ -887,6 +900,9 @@ __device__ __forceinline__ double get_range(double ox, double oy, double v3x, do
 }
 
 constexpr int POST_THREADS = 128;
+#ifndef POST_MIN_BLOCKS
+#define POST_MIN_BLOCKS 8
+#endif
 
 // Shared memory of one env inside a post_kernel CTA (doubles first, then ints; sized by A).
 struct EnvSmem {
@@ -894,54 +910,61 @@ struct EnvSmem {
     double (*pre)[3];    // [A]    Simulator.agent_poses: BEFORE iTTC zeroing (:587)
     double (*verts)[8];  // [A*A]  opponent b as seen by a: a's own length/width (:223)
     int* ind;            // [4*A*A] nearest beam of each vertex
-    int* lo;             // [A*A]  blocked-view window (get_blocked_view_indices)
-    int* hi;
-    int* cone;           // [4*A*A] beam-index intervals [f0, f1], [b0, b1] of the forward / backward cones
+    int* cone;           // [4*A*A] beam-index intervals of the forward / backward cones, before the clip to the window
     int* coll;           // [A]    GJK flags, later GJK | iTTC
     int* hit;            // [A]    iTTC flags
     int* lapdone;        // [A]
 };
-__host__ __device__ constexpr int post_smem_doubles(int A) { return 6 * A + 8 * A * A + (10 * A * A + 3 * A + 1) / 2; }
+__host__ __device__ constexpr int post_smem_doubles(int A) { return 6 * A + 8 * A * A + (8 * A * A + 3 * A + 1) / 2; }
 __device__ __forceinline__ EnvSmem env_smem(double* base, int A) {
     EnvSmem e;
     e.pose = reinterpret_cast<double (*)[3]>(base);
     e.pre = reinterpret_cast<double (*)[3]>(base + 3 * A);
     e.verts = reinterpret_cast<double (*)[8]>(base + 6 * A);
     e.ind = reinterpret_cast<int*>(base + 6 * A + 8 * A * A);
-    e.lo = e.ind + 4 * A * A;
-    e.hi = e.lo + A * A;
-    e.cone = e.hi + A * A;
+    e.cone = e.ind + 4 * A * A;
     e.coll = e.cone + 4 * A * A;
     e.hit = e.coll + A;
     e.lapdone = e.hit + A;
     return e;
 }
-// envs per CTA: enough of them that the 5 A^2 scalar work items of stage B fill the CTA's lanes
+// Envs per CTA: as many as keep (a) the 5.5 A (A - 1) scalar work items per env of stage B within one pass of the CTA's lanes
+// and (b) the 2 A ray-cast segments per env and round within one warp's scan (32).
 __host__ __device__ constexpr int post_envs_per_cta(int A) {
-    return (POST_THREADS / (5 * A * A)) < 1 ? 1 : ((POST_THREADS / (5 * A * A)) > 16 ? 16 : (POST_THREADS / (5 * A * A)));
+    const int by_items = (2 * POST_THREADS) / (11 * A * (A - 1)), by_segs = 16 / A;
+    const int e = by_items < by_segs ? by_items : by_segs;
+    return e < 1 ? 1 : e;
+}
+// ints of CTA-wide shared memory behind the per-env blocks: per round and segment, where its items start and its first beam
+__host__ __device__ constexpr int post_seg_ints(int A) { return (A - 1) * 2 * 33; }
+
+// The ordered pair (a, b != a) number p of A agents
+__device__ __forceinline__ void pair_of(int p, int A, int& a, int& b) {
+    a = p / (A - 1);
+    b = p - a * (A - 1);
+    b += b >= a ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
+__global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(SimConst c, SimState st, StepScratch sc, F110StepIO io) {
     cudaGridDependencySynchronize();
     const int A = c.A, B = c.B;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int epc = post_envs_per_cta(A);
     const int env0 = blockIdx.x * epc;
     extern __shared__ double s_dyn[];
     const int stride = post_smem_doubles(A);
+    int* const s_seg = reinterpret_cast<int*>(s_dyn + epc * stride);   // [A - 1][2][33]
     __shared__ int s_active[16];
-    if (tid < epc) {
-        const int env = env0 + tid;
-        s_active[tid] = env < c.N && !(io.active_mask && !io.active_mask[env]);
-    }
-    __syncthreads();
 
     // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252.  One thread per (env, agent).
     for (int t = tid; t < epc * A; t += POST_THREADS) {
         const int le = t / A, a = t - le * A;
-        if (!s_active[le]) continue;
+        const int env = env0 + le;
+        const bool active = env < c.N && !(io.active_mask && !io.active_mask[env]);
+        if (a == 0) s_active[le] = active;
+        if (!active) continue;
         const EnvSmem e = env_smem(s_dyn + le * stride, A);
-        const int s = (env0 + le) * A + a;
+        const int s = env * A + a;
         const int hit = sc.ttc_hit[s];
         const double px = st.x[0][s], py = st.x[1][s];
         const double yaw_pre = sc.pre_yaw[s];
@@ -953,16 +976,20 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
     }
     __syncthreads();
 
-    // ---- stage B: all-pairs GJK (check_collision :549-563) and the blocked-view window of every opponent b as seen
-    // from a (get_blocked_view_indices, laser_models.py:282-315): one thread per (env, a, b, vertex) and per GJK pair
-    const int nvert = A * A * 4, nitem = nvert + A * A;
+    // ---- stage B: everything scalar about a pair of cars, ALL of it in one pass (each item is a chain of a few thousand
+    // cycles of fp64 transcendentals; one item per lane): per ordered pair (a, b) the four vertices of b as a sees it with
+    // their nearest beams (get_blocked_view_indices, laser_models.py:282-315) and the cones its bounding circle spans;
+    // per unordered pair the GJK test (check_collision :549-563).
+    const int npair = A * (A - 1);
+    const int nvert = 4 * npair, ncone = npair, nitem = nvert + ncone + npair / 2;
     for (int t = tid; t < epc * nitem; t += POST_THREADS) {
-        const int le = t / nitem, u = t - le * nitem;
+        const int le = t / nitem, w = t - le * nitem;
         if (!s_active[le]) continue;
         const EnvSmem e = env_smem(s_dyn + le * stride, A);
-        if (u < nvert) {
-            const int a = u / (4 * A), b = (u >> 2) - a * A, k = u & 3;
-            if (a == b) continue;
+        if (w < nvert) {
+            int a, b;
+            pair_of(w >> 2, A, a, b);
+            const int k = w & 3, u = a * A + b;
             // vertex k of opponent b, a's own length/width (ray_cast_agents :223); order rl, rr, fr, fl
             const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
             double sb, cb;
@@ -971,8 +998,8 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
             const double hy = (k == 0 || k == 3) ? Wd / 2 : -Wd / 2;
             const double vxw = cb * hx + (-sb) * hy + e.pre[b][0];
             const double vyw = sb * hx + cb * hy + e.pre[b][1];
-            e.verts[a * A + b][2 * k] = vxw;
-            e.verts[a * A + b][2 * k + 1] = vyw;
+            e.verts[u][2 * k] = vxw;
+            e.verts[u][2 * k + 1] = vyw;
             // arctan2(sin(yaw), cos(yaw)) == yaw for the wrapped yaw and arctan2(v/|v|) == arctan2(v), each to an ulp; the
             // angle only selects the nearest beam, so the shorter dependent chain cannot change a window except at an
             // exact tie between two beams
@@ -981,65 +1008,93 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
             if (vx == 0. && vy == 0.) ang = nan("");   // the reference divides by the zero norm -> NaN -> argmin 0
             if (ang > F110_PI) ang = ang - 2 * F110_PI;
             else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
-            e.ind[u] = nearest_beam(c.scan_angles, B, -ang);
+            e.ind[4 * u + k] = nearest_beam(c.scan_angles, B, -ang);
+        } else if (w < nvert + ncone) {
+            int a, b;
+            pair_of(w - nvert, A, a, b);
+            const int u = a * A + b;
+            // The reference walks every beam of the window (all 1080 when the opponent is behind the car) although only
+            // beams whose LINE crosses the opponent can be lowered: a proper hit needs the ray to enter the car's bounding
+            // circle, and the collinear fallback of get_range (:270-274) needs the beam's line to contain an edge, forwards
+            // or backwards.  Beams further than alpha (+1e-6 rad) from both the bearing of the circle's centre and its
+            // opposite are never visited -- for them get_range returns inf on all four edges.
+            const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
+            const double R = 0.5 * sqrt(L * L + Wd * Wd) * (1.0 + 1e-9) + 1e-9;
+            const double dx = e.pre[b][0] - e.pose[a][0], dy = e.pre[b][1] - e.pose[a][1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            // cone -> beam-index intervals (supersets by one beam each side); the clip to the reference window follows in
+            // stage C, when the vertices' beams are known.  Default: no pruning, i.e. the whole window forwards.
+            int f0 = 0, f1 = B - 1, b0 = B, b1 = -1;
+            const double alpha = asin(R / dist) + 1e-6;
+            // beam angles lie inside [-fov/2, fov/2]: a cone of half-width < pi - fov/2 around a bearing in [-pi, pi] can only
+            // meet them un-wrapped (0.79 rad at the default 4.7 rad lidar; a lidar of 2 (pi - 0.05) rad or more is never pruned)
+            const double cone_max = fmin(0.75, F110_PI - 0.5 * c.fov - 0.01);
+            if (dist > R * (1.0 + 1e-6) && alpha < cone_max) {
+                double phi = atan2(dy, dx) - e.pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
+                if (phi > F110_PI) phi -= 2 * F110_PI;
+                else if (phi < -F110_PI) phi += 2 * F110_PI;
+                const double back = phi > 0. ? phi - F110_PI : phi + F110_PI;
+                const double amin = __ldg(c.scan_angles), amax = __ldg(c.scan_angles + B - 1);
+                if (phi + alpha < amin || phi - alpha > amax) { f0 = B; f1 = -1; }
+                else {
+                    f0 = nearest_beam(c.scan_angles, B, phi - alpha) - 1;
+                    f1 = nearest_beam(c.scan_angles, B, phi + alpha) + 1;
+                }
+                if (!(back + alpha < amin || back - alpha > amax)) {
+                    b0 = nearest_beam(c.scan_angles, B, back - alpha) - 1;
+                    b1 = nearest_beam(c.scan_angles, B, back + alpha) + 1;
+                }
+            }   // else: overlapping cars, NaN, or a cone too wide to reason about -> the whole reference window
+            e.cone[4 * u] = f0; e.cone[4 * u + 1] = f1; e.cone[4 * u + 2] = b0; e.cone[4 * u + 3] = b1;
         } else {
-            const int p = u - nvert, a = p / A, b = p - a * A;
-            if (a < b) {
-                double va[8], vb[8];
-                const double L = __ldg(c.sim_params + P_LENGTH), Wd = __ldg(c.sim_params + P_WIDTH);
-                get_vertices(e.pre[a][0], e.pre[a][1], e.pre[a][2], L, Wd, va);
-                get_vertices(e.pre[b][0], e.pre[b][1], e.pre[b][2], L, Wd, vb);
-                if (gjk_collision(va, vb)) { e.coll[a] = 1; e.coll[b] = 1; }
-            }
+            // unordered pair number p -> (a < b)
+            int p = w - nvert - ncone, a = 0;
+            while (p >= A - 1 - a) { p -= A - 1 - a; ++a; }
+            const int b = a + 1 + p;
+            double va[8], vb[8];
+            const double L = __ldg(c.sim_params + P_LENGTH), Wd = __ldg(c.sim_params + P_WIDTH);
+            get_vertices(e.pre[a][0], e.pre[a][1], e.pre[a][2], L, Wd, va);
+            get_vertices(e.pre[b][0], e.pre[b][1], e.pre[b][2], L, Wd, vb);
+            if (gjk_collision(va, vb)) { e.coll[a] = 1; e.coll[b] = 1; }
         }
     }
     __syncthreads();
-    for (int t = tid; t < epc * A * A; t += POST_THREADS) {
-        const int le = t / (A * A), u = t - le * A * A;
-        if (!s_active[le]) continue;
-        const EnvSmem e = env_smem(s_dyn + le * stride, A);
-        const int* q = e.ind + 4 * u;
-        const int a = u / A, b = u - a * A;
-        if (a == b) { e.lo[u] = B; e.hi[u] = -1; e.cone[4 * u] = B; e.cone[4 * u + 1] = -1; e.cone[4 * u + 2] = B; e.cone[4 * u + 3] = -1; continue; }
-        e.lo[u] = min(min(q[0], q[1]), min(q[2], q[3]));
-        e.hi[u] = max(max(q[0], q[1]), max(q[2], q[3]));
-        // The reference walks every beam of the window (all 1080 when the opponent is behind the car) although only
-        // beams whose LINE crosses the opponent can be lowered: a proper hit needs the ray to enter the car's bounding
-        // circle, and the collinear fallback of get_range (:270-274) needs the beam's line to contain an edge, forwards
-        // or backwards.  Beams further than alpha (+1e-6 rad) from both the bearing of the circle's centre and its
-        // opposite are never visited -- for them get_range returns inf on all four edges.
-        const double L = __ldg(c.params + a * F110_NUM_PARAMS + P_LENGTH), Wd = __ldg(c.params + a * F110_NUM_PARAMS + P_WIDTH);
-        const double R = 0.5 * sqrt(L * L + Wd * Wd) * (1.0 + 1e-9) + 1e-9;
-        const double dx = e.pre[b][0] - e.pose[a][0], dy = e.pre[b][1] - e.pose[a][1];
-        const double dist = sqrt(dx * dx + dy * dy);
-        // cone -> beam-index intervals (supersets by one beam each side), clipped to the reference window
-        int f0 = e.lo[u], f1 = e.hi[u], b0 = B, b1 = -1;
-        const double alpha = asin(R / dist) + 1e-6;
-        // beam angles lie inside [-fov/2, fov/2]: a cone of half-width < pi - fov/2 around a bearing in [-pi, pi] can only
-        // meet them un-wrapped (0.79 rad at the default 4.7 rad lidar; a lidar of 2 (pi - 0.05) rad or more is never pruned)
-        const double cone_max = fmin(0.75, F110_PI - 0.5 * c.fov - 0.01);
-        if (dist > R * (1.0 + 1e-6) && alpha < cone_max) {
-            double phi = atan2(dy, dx) - e.pose[a][2];           // in [-2 pi, 2 pi] -> [-pi, pi]
-            if (phi > F110_PI) phi -= 2 * F110_PI;
-            else if (phi < -F110_PI) phi += 2 * F110_PI;
-            const double back = phi > 0. ? phi - F110_PI : phi + F110_PI;
-            const double amin = __ldg(c.scan_angles), amax = __ldg(c.scan_angles + B - 1);
-            if (phi + alpha < amin || phi - alpha > amax) { f0 = B; f1 = -1; }
-            else {
-                f0 = max(f0, nearest_beam(c.scan_angles, B, phi - alpha) - 1);
-                f1 = min(f1, nearest_beam(c.scan_angles, B, phi + alpha) + 1);
-            }
-            if (!(back + alpha < amin || back - alpha > amax)) {
-                b0 = max(e.lo[u], nearest_beam(c.scan_angles, B, back - alpha) - 1);
-                b1 = min(e.hi[u], nearest_beam(c.scan_angles, B, back + alpha) + 1);
-                if (b0 <= f1 && f0 <= b1) { f0 = min(f0, b0); f1 = max(f1, b1); b0 = B; b1 = -1; }   // merge overlap
-            }
-        }   // else: overlapping cars, NaN, or a cone too wide to reason about -> the whole reference window
-        e.cone[4 * u] = f0; e.cone[4 * u + 1] = f1; e.cone[4 * u + 2] = b0; e.cone[4 * u + 3] = b1;
-    }
-    __syncthreads();
 
-    // ---- stage C: finish zone / laps per agent, _check_done f110_env.py:320-348
+    // ---- stage C, two jobs side by side.
+    // (1) The ray-cast's work list.  Car a meets its opponents in A - 1 ROUNDS, b = (a + k) mod A in round k, so that within
+    // a round every beam of every car is touched by at most one item (the minimum the reference forms opponent by
+    // opponent does not depend on their order).  Per round one warp turns the 2 A segments per env (forward and backward
+    // cone of the one opponent, clipped to the reference's window) into a prefix sum of their lengths.
+    const int nseg = epc * A * 2;     // <= 32
+    for (int k = 1 + wid; k < A; k += POST_THREADS / 32) {
+        int i0 = B, len = 0;
+        if (lane < nseg) {
+            const int le = lane / (2 * A), r = lane - le * 2 * A, a = r >> 1, half = r & 1;
+            if (s_active[le]) {
+                const EnvSmem e = env_smem(s_dyn + le * stride, A);
+                int b = a + k; b -= b >= A ? A : 0;
+                const int u = a * A + b;
+                const int* q = e.ind + 4 * u;
+                const int lo = min(min(q[0], q[1]), min(q[2], q[3])), hi = max(max(q[0], q[1]), max(q[2], q[3]));
+                int f0 = max(lo, e.cone[4 * u]), f1 = min(hi, e.cone[4 * u + 1]);
+                int b0 = max(lo, e.cone[4 * u + 2]), b1 = min(hi, e.cone[4 * u + 3]);
+                if (b0 <= f1 && f0 <= b1) { f0 = min(f0, b0); f1 = max(f1, b1); b0 = B; b1 = -1; }   // merge overlap
+                i0 = half ? b0 : f0;
+                len = max(0, (half ? b1 : f1) - i0 + 1);
+            }
+        }
+        int run = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int other = __shfl_up_sync(0xffffffffu, run, o);
+            if (lane >= o) run += other;
+        }
+        int* seg = s_seg + (k - 1) * 66;
+        seg[lane + 1] = run;             // seg[j] = first item of segment j, seg[32] = number of items
+        if (lane == 0) seg[0] = 0;
+        seg[33 + lane] = i0;
+    }
+    // (2) finish zone / laps per agent, _check_done f110_env.py:320-348
     for (int t = tid; t < epc * A; t += POST_THREADS) {
         const int le = t / A, a = t - le * A;
         if (!s_active[le]) continue;
@@ -1082,46 +1137,46 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(SimConst c, SimState
         }
         if (io.agent_poses) { double* o = io.agent_poses + (size_t)s * 3; o[0] = e.pre[a][0]; o[1] = e.pre[a][1]; o[2] = e.pre[a][2]; }
     }
+    __syncthreads();
 
     // ---- stage D: opponent ray-cast (ray_cast_agents :206-227).  The lidar kernel already wrote every scan; only the
-    // beams inside some opponent's blocked-view window can get shorter, so only those are re-read (fp64 scratch
-    // copy), lowered and re-written.
+    // beams inside some opponent's cone can get shorter, so only those are re-read (fp64 scratch copy), lowered and
+    // re-written -- one beam per lane, the items of all envs and cars of the CTA packed back to back.
     const float lm = c.lidar_max;
-    for (int le = 0; le < epc; ++le) {
-      if (!s_active[le]) continue;
-      const EnvSmem e = env_smem(s_dyn + le * stride, A);
-      const int env = env0 + le;
-      for (int a = 0, u = 0; a < A; ++a)
-      for (int b = 0; b < A; ++b, ++u) {           // nested counters: no integer divisions in this 24-trip loop
-        if (a == b) continue;
-        const double* v = e.verts[u];
+    for (int k = 1; k < A; ++k) {
+        const int* seg = s_seg + (k - 1) * 66;
+        const int total = seg[32];
+        for (int it = tid; it < total; it += POST_THREADS) {
+            // the segment holding item `it`: the last j with seg[j] <= it (empty segments repeat a start and are skipped)
+            int j = 0;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i0 = e.cone[4 * u + 2 * half], i1 = e.cone[4 * u + 2 * half + 1];
-            // beam i always belongs to thread i % POST_THREADS, so successive opponents of the same car lower a beam
-            // through the same thread, in the reference's order, via the scratch copy
-            for (int i = (i0 & ~(POST_THREADS - 1)) + tid; i <= i1; i += POST_THREADS) {
-                if (i < i0) continue;
-                const size_t g = (size_t)(env * A + a) * B + i;
-                const double range0 = sc.scan[g];
-                double range = range0;
-                double v3x, v3y;
-                sincos(e.pose[a][2] + __ldg(c.scan_angles + i) + F110_PI / 2., &v3y, &v3x);
+            for (int step = 16; step > 0; step >>= 1) j += (j + step < 32 && seg[j + step] <= it) ? step : 0;
+            const int le = j / (2 * A), a = (j - le * 2 * A) >> 1;
+            int b = a + k; b -= b >= A ? A : 0;
+            const EnvSmem e = env_smem(s_dyn + le * stride, A);
+            const double* v = e.verts[a * A + b];
+            const int i = seg[33 + j] + (it - seg[j]);
+            const int env = env0 + le;
+            const size_t g = (size_t)(env * A + a) * B + i;
+            const double range0 = sc.scan[g];
+            double range = range0;
+            double v3x, v3y;
+            sincos(e.pose[a][2] + __ldg(c.scan_angles + i) + F110_PI / 2., &v3y, &v3x);
+            const double ox = e.pose[a][0], oy = e.pose[a][1];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int j2 = (j + 1) & 3;
-                    const double rr = get_range(e.pose[a][0], e.pose[a][1], v3x, v3y, v[2 * j], v[2 * j + 1], v[2 * j2], v[2 * j2 + 1]);
-                    if (rr < range) range = rr;
-                }
-                if (range < range0) {
-                    sc.scan[g] = range;
-                    if (io.scans_f64) io.scans_f64[g] = range;
-                    if (io.scans_f32) io.scans_f32[g] = (float)range;
-                    if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar<false>(range, lm, 0.0f);
-                }
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j2 = (jj + 1) & 3;
+                const double rr = get_range(ox, oy, v3x, v3y, v[2 * jj], v[2 * jj + 1], v[2 * j2], v[2 * j2 + 1]);
+                if (rr < range) range = rr;
+            }
+            if (range < range0) {
+                sc.scan[g] = range;
+                if (io.scans_f64) io.scans_f64[g] = range;
+                if (io.scans_f32) io.scans_f32[g] = (float)range;
+                if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar<false>(range, lm, 0.0f);
             }
         }
-      }
+        if (k + 1 < A) __syncthreads();   // the next round re-reads what this one lowered
     }
     __syncthreads();
 
@@ -1284,7 +1339,8 @@ cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st
 cudaError_t launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s) {
     if (c.A == 1) return launch_pdl(post_single_kernel, dim3((c.N + 127) / 128), dim3(128), 0, s, c, st, sc, io);
     const int epc = post_envs_per_cta(c.A);
-    return launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS), sizeof(double) * post_smem_doubles(c.A) * epc, s, c, st, sc, io);
+    return launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS),
+                      sizeof(double) * post_smem_doubles(c.A) * epc + sizeof(int) * post_seg_ints(c.A), s, c, st, sc, io);
 }
 
 cudaError_t launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {

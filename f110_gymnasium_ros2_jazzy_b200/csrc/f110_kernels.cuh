@@ -122,6 +122,15 @@ cudaError_t launch_sim_reset(const SimConst& c, const SimState& st, const double
 // dense [H][W] -> padded [prows][pitch] with the sentinel -1.0 outside the map (both DEVICE pointers)
 cudaError_t launch_pad_map(const double* dense, int H, int W, double* padded, int prows, int pitch, cudaStream_t s);
 
-// exact EDT on the device (f110_edt.cu): freemask DEVICE [H][W] (non-zero = free), dt DEVICE fp64 [H][W]; synchronises
-int edt_device(const uint8_t* freemask, int H, int W, double resolution, double* dt, cudaStream_t stream);
+// exact EDT on the device (f110_edt.cu): freemask DEVICE [H][W] (non-zero = free), dt DEVICE fp64 [H][W]; synchronises.
+// The scratch (12 bytes per cell) stays with the caller's handle and is reused by the next call.
+struct EdtScratch {
+    void* base = nullptr;
+    size_t bytes = 0;
+    void* ev0 = nullptr;
+    void* ev1 = nullptr;
+    float kernel_ms = 0.f;   // the EDT kernels of the last call, by CUDA events
+};
+int edt_device(const uint8_t* freemask, int H, int W, double resolution, double* dt, EdtScratch* scratch, cudaStream_t stream);
+void edt_scratch_free(EdtScratch* scratch);
 int f110_set_error(int code, const char* msg);   // sets the thread-local message of f110_last_error(); returns code

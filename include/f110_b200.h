@@ -145,6 +145,8 @@ int f110_set_map(F110Sim* sim, const double* dt, int32_t height, int32_t width, 
  * the device in integers; the resulting fp64 map is bit-identical to resolution * distance_transform_edt(img). */
 int f110_set_map_image(F110Sim* sim, const uint8_t* free_mask, int32_t height, int32_t width, double resolution,
                        double orig_x, double orig_y, double orig_cos, double orig_sin);
+/* Device time of the EDT kernels of the last f110_set_map_image call on this handle, in ms (CUDA events); 0 before any. */
+float f110_edt_kernel_ms(const F110Sim* sim);
 /* Reads the handle's fp64 map back into dt_host (capacity in cells). */
 int f110_get_map(F110Sim* sim, double* dt_host, int64_t capacity_cells);
 /* HOST [theta_dis] tables (laser_models.py:379-381). */

@@ -1008,12 +1008,20 @@ def test_device_edt_bit_identical_to_scipy():
         got = sim.get_map()
         assert got.shape == ref.shape and np.array_equal(got, ref), name
     rng = np.random.default_rng(4)
-    for shape, p in (((257, 131), 0.01), ((64, 700), 0.2), ((300, 300), 0.0005), ((5, 1000), 0.05)):
+    for shape, p in (((257, 131), 0.01), ((64, 700), 0.2), ((300, 300), 0.0005), ((5, 1000), 0.05), ((1, 77), 0.1), ((200, 1), 0.05),
+                     ((130, 1030), 0.00002)):
         free = (rng.uniform(size=shape) > p).astype(np.uint8)
         free[rng.integers(0, shape[0]), rng.integers(0, shape[1])] = 0      # at least one obstacle
         ref = 0.0731 * distance_transform_edt(np.where(free, 255., 0.))
-        sim.set_map_image(free, 0.0731, [0.0, 0.0, 0.0])
-        assert np.array_equal(sim.get_map(), ref), shape
+        # both forms: the banded 16-bit kernels every real map takes, and the general one (H + W > 32766), forced
+        for wide in ('0', '1'):
+            os.environ['F110_EDT_WIDE'] = wide
+            try:
+                sim.set_map_image(free, 0.0731, [0.0, 0.0, 0.0])
+            finally:
+                os.environ.pop('F110_EDT_WIDE')
+            assert np.array_equal(sim.get_map(), ref), (shape, wide)
+        assert sim.edt_kernel_ms() > 0.0
     # and the scans taken on a device-built map equal the ones on the host-built map
     g = H.load('scans')
     poses = g['Shanghai_map__poses']
