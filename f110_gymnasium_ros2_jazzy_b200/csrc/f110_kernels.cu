@@ -442,7 +442,10 @@ __device__ __forceinline__ float obs_lidar(double range, float lm, float rcp) {
 #ifndef HEAVY_T2
 #define HEAVY_T2 24u
 #endif
-constexpr int LIDAR_THREADS = 128;
+#ifndef LIDAR_THREADS_OVERRIDE
+#define LIDAR_THREADS_OVERRIDE 128
+#endif
+constexpr int LIDAR_THREADS = LIDAR_THREADS_OVERRIDE;
 #ifndef LIDAR_MIN_BLOCKS
 #define LIDAR_MIN_BLOCKS 12
 #endif
@@ -545,7 +548,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
     resolve(pos, unit, skip);
     while (pos < npos) {
         unsigned nlook = 0;
-        bool live = false;
+        bool live = false, redone_here = false;
         unsigned npos_next, nunit; bool nskip;
         if (!skip) {
             unsigned t_start = 0;
@@ -642,7 +645,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                     const double2 ex = trace_ray_exact(m, c, sc, s, ti);
                     total_d = ex.x;
                     nlook = (unsigned)ex.y;
-                    if (COUNT) ++cnt_redone;
+                    if (COUNT) { ++cnt_redone; redone_here = true; }
                 }
                 if (total_d > c.max_range) total_d = c.max_range;
             }
@@ -713,11 +716,12 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 resolve(npos_next, nunit, nskip);
             }
             if (COUNT) {
+                const unsigned redo_lanes = __popc(__ballot_sync(0xffffffffu, redone_here));   // timeline: bits 24.. of the lookup word
                 if (sc.timeline && lane == 0) {
                     unsigned t_end, smid;
                     asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_end));
                     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                    sc.timeline[unit] = make_uint4(t_start, t_end, wmax, (smid << 24) | (pos & 0xFFFFFFu));
+                    sc.timeline[unit] = make_uint4(t_start, t_end, wmax | (redo_lanes << 24), (smid << 24) | (pos & 0xFFFFFFu));
                 }
                 cnt_look += nlook;
                 cnt_rays += live ? 1u : 0u;
@@ -746,20 +750,20 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
 
 // ---------------------------------------------------------------- K3: post
 
-// End of a step's lidar bookkeeping, done by the post kernel: the last block to finish (ticket counter) latches the
-// recorded counts, flips the parity and rewinds the queue.
+// End of a step's lidar bookkeeping, done by one thread of the post kernel: latch the recorded counts, flip the parity and
+// rewind the queue.  Everything it touches was written by the lidar kernel, which is complete before the post kernel's
+// first instruction (cudaGridDependencySynchronize), and is next read by the following step's kernels, which wait for
+// this grid in the same way -- no fence, no ticket.
 __device__ __forceinline__ void latch_launch_order(const StepScratch& sc) {
-    __threadfence();
-    if (threadIdx.x != 0) return;
-    if (atomicAdd(sc.ctrl + CTRL_TICKET, 1u) != gridDim.x - 1u) return;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-        const unsigned n = atomicExch(sc.ctrl + CTRL_NEXT + b * CTRL_NEXT_STRIDE, 0u);
+        const unsigned n = sc.ctrl[CTRL_NEXT + b * CTRL_NEXT_STRIDE];
+        sc.ctrl[CTRL_NEXT + b * CTRL_NEXT_STRIDE] = 0u;
         sc.ctrl[CTRL_CUR + b] = n < sc.cap[b] ? n : sc.cap[b];
     }
     sc.ctrl[CTRL_EPOCH] += 1u;
     sc.ctrl[CTRL_POS] = 0u;
-    sc.ctrl[CTRL_TICKET] = 0u;
 }
 
 // get_trmtx + get_vertices, collision_models.py:218-260; order rl, rr, fr, fl
@@ -850,20 +854,20 @@ __device__ bool gjk_collision(const double* v1, const double* v2) {
 // uniform table would give and walk; ties resolve to the lower index, as argmin does.
 __device__ __forceinline__ int nearest_beam(const double* __restrict__ ang, int B, double a) {
     if (a != a) return 0;
-    const double a0 = __ldg(ang), a1 = __ldg(ang + B - 1);
+    const double a0 = ang[0], a1 = ang[B - 1];
     double g = (a - a0) / (a1 - a0) * (double)(B - 1);
     g = g < 0. ? 0. : (g > (double)(B - 1) ? (double)(B - 1) : g);
     int k = (int)(g + 0.5);
     // the three candidates of a uniform table, loaded together
     const int km = k > 0 ? k - 1 : 0, kp = k + 1 < B ? k + 1 : B - 1;
-    double dm = fabs(__ldg(ang + km) - a), dk = fabs(__ldg(ang + k) - a), dp = fabs(__ldg(ang + kp) - a);
+    double dm = fabs(ang[km] - a), dk = fabs(ang[k] - a), dp = fabs(ang[kp] - a);
     if (dp < dk) { k = kp; dk = dp; } else if (dm <= dk && km != k) { k = km; dk = dm; }
     while (k + 1 < B) {
-        const double dn = fabs(__ldg(ang + k + 1) - a);
+        const double dn = fabs(ang[k + 1] - a);
         if (dn < dk) { ++k; dk = dn; } else break;
     }
     while (k > 0) {
-        const double dn = fabs(__ldg(ang + k - 1) - a);
+        const double dn = fabs(ang[k - 1] - a);
         if (dn <= dk) { --k; dk = dn; } else break;
     }
     return k;
@@ -903,6 +907,9 @@ constexpr int POST_THREADS = 128;
 #ifndef POST_MIN_BLOCKS
 #define POST_MIN_BLOCKS 8
 #endif
+#ifndef POST_EPC_CAP
+#define POST_EPC_CAP 16      // tuning: upper bound on the envs per CTA
+#endif
 
 // Shared memory of one env inside a post_kernel CTA (doubles first, then ints; sized by A).
 struct EnvSmem {
@@ -933,10 +940,15 @@ __device__ __forceinline__ EnvSmem env_smem(double* base, int A) {
 __host__ __device__ constexpr int post_envs_per_cta(int A) {
     const int by_items = (2 * POST_THREADS) / (11 * A * (A - 1)), by_segs = 16 / A;
     const int e = by_items < by_segs ? by_items : by_segs;
-    return e < 1 ? 1 : e;
+    return e < 1 ? 1 : (e > POST_EPC_CAP ? POST_EPC_CAP : e);
 }
 // ints of CTA-wide shared memory behind the per-env blocks: per round and segment, where its items start and its first beam
 __host__ __device__ constexpr int post_seg_ints(int A) { return (A - 1) * 2 * 33; }
+// The beam-angle table is staged in shared memory (in front of the per-env blocks) when it is at most this long: the
+// nearest-beam searches are chains of dependent table reads -- 16 of them in a row in a cone item -- and from L2 they were
+// the longest thing a CTA did.
+constexpr int POST_STAGED_BEAMS = 2048;   // 16 KB: with 16 agents the CTA still fits the 48 KB that need no opt-in
+__host__ __device__ constexpr int post_angle_doubles(int B) { return B <= POST_STAGED_BEAMS ? B : 0; }
 
 // The ordered pair (a, b != a) number p of A agents
 __device__ __forceinline__ void pair_of(int p, int A, int& a, int& b) {
@@ -951,10 +963,16 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int epc = post_envs_per_cta(A);
     const int env0 = blockIdx.x * epc;
-    extern __shared__ double s_dyn[];
+    extern __shared__ double s_all[];
+    double* const s_dyn = s_all + post_angle_doubles(B);
     const int stride = post_smem_doubles(A);
     int* const s_seg = reinterpret_cast<int*>(s_dyn + epc * stride);   // [A - 1][2][33]
     __shared__ int s_active[16];
+    const double* angles = c.scan_angles;
+    if (post_angle_doubles(B)) {
+        for (int k = tid; k < B; k += POST_THREADS) s_all[k] = __ldg(c.scan_angles + k);
+        angles = s_all;
+    }
 
     // ---- stage A: iTTC consequences, RaceCar.check_ttc base_classes.py:243-252.  One thread per (env, agent).
     for (int t = tid; t < epc * A; t += POST_THREADS) {
@@ -980,10 +998,20 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
     // cycles of fp64 transcendentals; one item per lane): per ordered pair (a, b) the four vertices of b as a sees it with
     // their nearest beams (get_blocked_view_indices, laser_models.py:282-315) and the cones its bounding circle spans;
     // per unordered pair the GJK test (check_collision :549-563).
+    // The three kinds of item sit in different warps where that still fits one pass (a warp that held all three would run
+    // them one after the other).
     const int npair = A * (A - 1);
-    const int nvert = 4 * npair, ncone = npair, nitem = nvert + ncone + npair / 2;
-    for (int t = tid; t < epc * nitem; t += POST_THREADS) {
-        const int le = t / nitem, w = t - le * nitem;
+    const int nvert = 4 * npair, ncone = npair, ngjk = npair / 2;
+    int oC = epc * nvert, oG = oC + epc * ncone;
+    {
+        const int pC = (oC + 31) & ~31, pG = (pC + epc * ncone + 31) & ~31;
+        if (pG + epc * ngjk <= POST_THREADS) { oC = pC; oG = pG; }
+    }
+    for (int t = tid; t < oG + epc * ngjk; t += POST_THREADS) {
+        int le, w;
+        if (t < oC) { if (t >= epc * nvert) continue; le = t / nvert; w = t - le * nvert; }
+        else if (t < oG) { if (t - oC >= epc * ncone) continue; le = (t - oC) / ncone; w = nvert + (t - oC) - le * ncone; }
+        else { le = (t - oG) / ngjk; w = nvert + ncone + (t - oG) - le * ngjk; }
         if (!s_active[le]) continue;
         const EnvSmem e = env_smem(s_dyn + le * stride, A);
         if (w < nvert) {
@@ -1008,7 +1036,7 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
             if (vx == 0. && vy == 0.) ang = nan("");   // the reference divides by the zero norm -> NaN -> argmin 0
             if (ang > F110_PI) ang = ang - 2 * F110_PI;
             else if (ang < -F110_PI) ang = ang + 2 * F110_PI;
-            e.ind[4 * u + k] = nearest_beam(c.scan_angles, B, -ang);
+            e.ind[4 * u + k] = nearest_beam(angles, B, -ang);
         } else if (w < nvert + ncone) {
             int a, b;
             pair_of(w - nvert, A, a, b);
@@ -1034,15 +1062,15 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
                 if (phi > F110_PI) phi -= 2 * F110_PI;
                 else if (phi < -F110_PI) phi += 2 * F110_PI;
                 const double back = phi > 0. ? phi - F110_PI : phi + F110_PI;
-                const double amin = __ldg(c.scan_angles), amax = __ldg(c.scan_angles + B - 1);
+                const double amin = angles[0], amax = angles[B - 1];
                 if (phi + alpha < amin || phi - alpha > amax) { f0 = B; f1 = -1; }
                 else {
-                    f0 = nearest_beam(c.scan_angles, B, phi - alpha) - 1;
-                    f1 = nearest_beam(c.scan_angles, B, phi + alpha) + 1;
+                    f0 = nearest_beam(angles, B, phi - alpha) - 1;
+                    f1 = nearest_beam(angles, B, phi + alpha) + 1;
                 }
                 if (!(back + alpha < amin || back - alpha > amax)) {
-                    b0 = nearest_beam(c.scan_angles, B, back - alpha) - 1;
-                    b1 = nearest_beam(c.scan_angles, B, back + alpha) + 1;
+                    b0 = nearest_beam(angles, B, back - alpha) - 1;
+                    b1 = nearest_beam(angles, B, back + alpha) + 1;
                 }
             }   // else: overlapping cars, NaN, or a cone too wide to reason about -> the whole reference window
             e.cone[4 * u] = f0; e.cone[4 * u + 1] = f1; e.cone[4 * u + 2] = b0; e.cone[4 * u + 3] = b1;
@@ -1161,7 +1189,7 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
             const double range0 = sc.scan[g];
             double range = range0;
             double v3x, v3y;
-            sincos(e.pose[a][2] + __ldg(c.scan_angles + i) + F110_PI / 2., &v3y, &v3x);
+            sincos(e.pose[a][2] + angles[i] + F110_PI / 2., &v3y, &v3x);
             const double ox = e.pose[a][0], oy = e.pose[a][1];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -1340,7 +1368,7 @@ cudaError_t launch_post(const SimConst& c, const SimState& st, const StepScratch
     if (c.A == 1) return launch_pdl(post_single_kernel, dim3((c.N + 127) / 128), dim3(128), 0, s, c, st, sc, io);
     const int epc = post_envs_per_cta(c.A);
     return launch_pdl(post_kernel, dim3((c.N + epc - 1) / epc), dim3(POST_THREADS),
-                      sizeof(double) * post_smem_doubles(c.A) * epc + sizeof(int) * post_seg_ints(c.A), s, c, st, sc, io);
+                      sizeof(double) * (post_angle_doubles(c.B) + post_smem_doubles(c.A) * epc) + sizeof(int) * post_seg_ints(c.A), s, c, st, sc, io);
 }
 
 cudaError_t launch_sim_reset(const SimConst& c, const SimState& st, const double* poses, const uint8_t* mask, cudaStream_t s) {

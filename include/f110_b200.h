@@ -204,7 +204,7 @@ int64_t f110_max_lookups(const F110Sim* sim);
  * decide (cell-edge guard band, map border and beyond, non-finite pose), as of the last f110_get_lookup_count call. */
 int64_t f110_redone_rays(const F110Sim* sim);
 /* Development aid (requires F110_FLAG_COUNT_LOOKUPS): per work unit of the last lidar launch, 4 words (start ns, end ns,
- * both the low half of %globaltimer; longest ray in lookups; sm << 24 | queue position).  out == NULL returns the number
+ * both the low half of %globaltimer; longest ray in lookups | lanes redone exactly << 24; sm << 24 | queue position).  out == NULL returns the number
  * of units (0 when no timeline is kept); otherwise copies [units][4] words and returns the count, or a negative error. */
 int64_t f110_debug_unit_timeline(F110Sim* sim, uint32_t* out, int64_t capacity_units);
 /* Incremented by every successful f110_set_map / f110_set_map_image.  The step kernels receive the map descriptor by

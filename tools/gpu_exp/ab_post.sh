@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of library builds on the two-car shape (post_kernel): every tools/gpu_exp/libs/*.so runs 8192 two-car envs and 4096 four-car envs.
 cd "$(dirname "$0")/../.."
-for lib in tools/gpu_exp/libs/*.so; do
+for lib in tools/gpu_exp/libs/${1:-*}.so; do
   name=$(basename $lib .so)
   export F110_B200_LIB=$PWD/$lib
   for cfg in "2 8192" "4 4096"; do

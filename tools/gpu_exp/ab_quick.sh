@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of library builds: every tools/gpu_exp/libs/*.so (selected through F110_B200_LIB) runs the C3 bench at three batch sizes.
 cd "$(dirname "$0")/../.."
-for lib in tools/gpu_exp/libs/*.so; do
+for lib in tools/gpu_exp/libs/${1:-*}.so; do
   name=$(basename $lib .so)
   export F110_B200_LIB=$PWD/$lib
   for envs in 512 4096 32768; do

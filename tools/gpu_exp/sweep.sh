@@ -24,7 +24,13 @@ row "C4: 32768 envs, B=2160" --envs 32768 --beams 2160
 row "C4: 32768 envs, B=4320" --envs 32768 --beams 4320
 row "C4: 32768 envs, Shanghai x2 (4000^2, 128 MB)" --envs 32768 --map-upsample 2
 row "C4: 32768 envs, Shanghai x4 (8000^2, 512 MB)" --envs 32768 --map-upsample 4
+row "C4 at full size: 262144 envs, B=270" --config c4 --beams 270
+row "C4 at full size: 262144 envs, B=2160" --config c4 --beams 2160
+row "C4 at full size: 262144 envs, B=4320" --config c4 --beams 4320
+row "C4 at full size: 262144 envs, Shanghai x2 (4000^2)" --config c4 --map-upsample 2
+row "C4 at full size: 262144 envs, Shanghai x4 (8000^2)" --config c4 --map-upsample 4
 row "C5 shape: 8192 envs, A=2" --envs 8192 --agents 2
+row "4096 envs, A=4" --envs 4096 --agents 4
 python - <<'PY'
 import json
 g = json.load(open("gpurun_out/sweep.json"))["roofline"]["gather_roofline"]

@@ -43,10 +43,10 @@ def main():
     t0 = buf[:, 0].astype(np.int64); t1 = buf[:, 1].astype(np.int64)
     base = t0.min()
     s, e = (t0 - base) / 1e3, (t1 - base) / 1e3        # us
-    look, sm, pos = buf[:, 2], buf[:, 3] >> 24, buf[:, 3] & 0xFFFFFF
+    look, redo, sm, pos = buf[:, 2] & 0xFFFFFF, buf[:, 2] >> 24, buf[:, 3] >> 24, buf[:, 3] & 0xFFFFFF
     dur = e - s
     os.makedirs('gpurun_out', exist_ok=True)
-    np.savez_compressed('gpurun_out/unit_timeline_%d.npz' % a.envs, start_us=s, end_us=e, lookups=look, sm=sm, pos=pos)
+    np.savez_compressed('gpurun_out/unit_timeline_%d.npz' % a.envs, start_us=s, end_us=e, lookups=look, sm=sm, pos=pos, redo=redo)
     print("units %d, kernel span (first unit start -> last unit end) %.1f us" % (n, e.max()))
     print("sum of unit durations %.0f us = %.1f us per warp slot over %d slots" % (dur.sum(), dur.sum() / (148 * 48), 148 * 48))
     order = np.argsort(-look.astype(np.int64))[:8]
@@ -64,6 +64,12 @@ def main():
         sel = (look >= lo) & (look < hi)
         if sel.any():
             print("  lookups [%3d,%4d): %6d units, mean %.2f us, start median %.1f us" % (lo, hi, sel.sum(), dur[sel].mean(), np.median(s[sel])))
+    r = redo > 0
+    if r.any():
+        print("units with rays redone in exact arithmetic: %d, mean %.2f us (%.0f ns/lookup) against %.2f us (%.0f ns/lookup) for the others below 24 lookups"
+              % (r.sum(), dur[r].mean(), 1e3 * dur[r].sum() / look[r].sum(), dur[~r & (look < 24)].mean(),
+                 1e3 * dur[~r & (look < 24)].sum() / look[~r & (look < 24)].sum()))
+        print("  of the 50 units that finish last, %d had a redone ray" % int(r[np.argsort(-e)[:50]].sum()))
     per_sm = np.bincount(sm, weights=dur, minlength=148)
     print("per-SM busy warp-us: min %.0f mean %.0f max %.0f" % (per_sm.min(), per_sm.mean(), per_sm.max()))
 
