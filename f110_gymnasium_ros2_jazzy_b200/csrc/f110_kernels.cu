@@ -452,6 +452,9 @@ constexpr int LIDAR_THREADS = LIDAR_THREADS_OVERRIDE;
 #ifndef LIDAR_CHUNK_OVERRIDE
 #define LIDAR_CHUNK_OVERRIDE 4
 #endif
+#ifndef LIDAR_MIN_TAKE
+#define LIDAR_MIN_TAKE 2u     // positions per fetch in the last stretch of the light region (see `fetch`)
+#endif
 constexpr unsigned LIDAR_CHUNK = LIDAR_CHUNK_OVERRIDE;   // queue positions a warp takes per fetch in the bulk of the light region
 
 // K2.  One thread per beam; a UNIT is 32 consecutive beams of one scan (the last unit of a scan is partly empty: 1080
@@ -537,11 +540,14 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
     // the first position of every warp is its own index: the counter starts at 0 and a fetch returns old + nwarps
     unsigned pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, end = pos + 1u;
     unsigned f = 0, take = 1u;
-    // guided self-scheduling: half of an even share of what is left, between 1 and LIDAR_CHUNK positions; one at a time in
-    // the heavy lists, where a unit is long and balance matters most
+    // guided self-scheduling: half of an even share of what is left, between LIDAR_MIN_TAKE and LIDAR_CHUNK positions; one at a
+    // time in the heavy lists, where a unit is long and balance matters most.  Not one at a time at the end of the light
+    // region: a fetch is an L2 atomic's round trip plus the class lookup behind it (1.9 us when every unit pays it: unit
+    // timeline with LIDAR_CHUNK 1), a light unit is 3.3 us, and all 7 104 warps asking after every unit is more than the
+    // one counter serves (about 1.4 fetches per ns) -- two at a time costs 1.6 us of balance and was 3 % faster at 4096 envs.
     auto fetch = [&](unsigned at) {
-        take = at < n2 ? 1u : (npos - at) / (2u * nwarps);
-        take = take < 1u ? 1u : (take > (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) ? (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) : take);
+        take = (npos - at) / (2u * nwarps);
+        take = at < n2 ? 1u : take < LIDAR_MIN_TAKE ? LIDAR_MIN_TAKE : (take > (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) ? (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) : take);
         if (lane == 0) f = atomicAdd(qpos, take) + nwarps;
     };
     unsigned unit; bool skip;
