@@ -63,6 +63,7 @@ struct F110Sim {
     bool count_lookups = false;
     bool narrow_fraction = false;
     bool debug_sync = false;
+    bool lidar_tile = false;      // F110_LIDAR_TILE=1: the shared-memory tile experiment of the lidar kernel (see lidar_tile_kernel)
     // device memory
     char* state_blob = nullptr;   size_t state_bytes = 0;    // checkpointable
     char* scratch_blob = nullptr; size_t scratch_bytes = 0;
@@ -158,7 +159,7 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
     CUDA_TRY(launch_dynamics(sim->c, sim->map, sim->st, sim->sc, io, s));
     DEBUG_SYNC("dynamics_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[1], s));
-    CUDA_TRY(launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_blocks, s));
+    CUDA_TRY(launch_lidar(sim->c, sim->map, sim->st, sim->sc, io, sim->count_lookups, sim->lidar_blocks, sim->lidar_tile, s));
     DEBUG_SYNC("lidar_kernel")
     if (sim->timing) CUDA_TRY(cudaEventRecord(e[2], s));
     CUDA_TRY(launch_post(sim->c, sim->st, sim->sc, io, s));
@@ -206,6 +207,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->count_lookups = (cfg->flags & F110_FLAG_COUNT_LOOKUPS) != 0;
     sim->narrow_fraction = (cfg->flags & F110_FLAG_NARROW_FRACTION) != 0;
     sim->debug_sync = getenv("F110_DEBUG_SYNC") != nullptr;
+    { const char* t = getenv("F110_LIDAR_TILE"); sim->lidar_tile = t && t[0] == '1'; }
     sim->lidar_blocks = lidar_resident_blocks(A == 1);
     sim->sc.ordered = 0;   // set below, once the unit count is known
     if (sim->lidar_blocks < 1) {

@@ -114,7 +114,7 @@ struct SimConst {
 cudaError_t launch_dynamics(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s);
 int lidar_resident_blocks(bool single_agent);
 cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st, const StepScratch& sc, const F110StepIO& io,
-                         bool count_lookups, int resident_blocks, cudaStream_t s);
+                         bool count_lookups, int resident_blocks, bool tile_experiment, cudaStream_t s);
 // smallest positive value of a dense device map (set_map time); synchronises the stream
 cudaError_t map_min_positive(const double* dense, size_t cells, double* out, cudaStream_t s);
 cudaError_t launch_post(const SimConst& c, const SimState& st, const StepScratch& sc, const F110StepIO& io, cudaStream_t s);
