@@ -104,7 +104,6 @@ void layout_scratch(Arena& a, StepScratch& sc, int NA, int B, bool timeline) {
     sc.ttc_hit = a.take<int32_t>(NA);
     sc.lookups = a.take<unsigned long long>(4);
     sc.stats = a.take<double>(F110_NUM_STATS);
-    sc.scan = a.take<double>((size_t)NA * B);
     sc.num_units = (unsigned)((size_t)NA * ((B + 31) / 32));
     // capacities of the three heavy-unit lists (classes >= 96 / 48 / 24 lookups); a list that overflows sends the rest of
     // its class to the light region, which costs order, never correctness

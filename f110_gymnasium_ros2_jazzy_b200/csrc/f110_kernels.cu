@@ -677,7 +677,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                     range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
                 }
                 // The scan goes straight to the caller's buffers.  With opponents (A >= 2) the post kernel lowers the few
-                // beams that hit another car afterwards, from the fp64 copy kept in scratch.
+                // beams that hit another car afterwards, in those same buffers.
                 // Streaming stores (evict-first): nothing in this kernel reads the outputs back, and at 32 768 envs the
                 // 142 MB of observations would otherwise push the map out of L2 (2.5 % of the kernel there).
                 if (io.scans_f64) __stcs(io.scans_f64 + r, range);
@@ -685,7 +685,6 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 if (DIRECT) {
                     if (io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 } else {
-                    sc.scan[r] = range;
                     if (io.obs && s == env * (unsigned)c.A)
                         __stcs(io.obs + (size_t)env * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 }
@@ -1322,8 +1321,8 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
     __syncthreads();
 
     // ---- stage D: opponent ray-cast (ray_cast_agents :206-227).  The lidar kernel already wrote every scan; only the
-    // beams inside some opponent's cone can get shorter, so only those are re-read (fp64 scratch copy), lowered and
-    // re-written -- one beam per lane, the items of all envs and cars of the CTA packed back to back.
+    // beams inside some opponent's cone can get shorter, so only those are re-read, lowered and re-written -- one beam per
+    // lane, the items of all envs and cars of the CTA packed back to back.
     const float lm = c.lidar_max;
     for (int k = 1; k < A; ++k) {
         const int* seg = s_seg + (k - 1) * 66;
@@ -1340,22 +1339,37 @@ __global__ void __launch_bounds__(POST_THREADS, POST_MIN_BLOCKS) post_kernel(Sim
             const int i = seg[33 + j] + (it - seg[j]);
             const int env = env0 + le;
             const size_t g = (size_t)(env * A + a) * B + i;
-            const double range0 = sc.scan[g];
-            double range = range0;
             double v3x, v3y;
             sincos(e.pose[a][2] + angles[i] + F110_PI / 2., &v3y, &v3x);
             const double ox = e.pose[a][0], oy = e.pose[a][1];
+            double best = INFINITY;      // where this beam meets the opponent, if it does
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j2 = (jj + 1) & 3;
                 const double rr = get_range(ox, oy, v3x, v3y, v[2 * jj], v[2 * jj + 1], v[2 * j2], v[2 * j2 + 1]);
-                if (rr < range) range = rr;
+                if (rr < best) best = rr;
             }
-            if (range < range0) {
-                sc.scan[g] = range;
-                if (io.scans_f64) io.scans_f64[g] = range;
-                if (io.scans_f32) io.scans_f32[g] = (float)range;
-                if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar<false>(range, lm, 0.0f);
+            // scan[i] = min(scan[i], best), in the caller's buffers (the lidar kernel wrote them).  With an fp64 scan
+            // among the outputs that is the reference's statement; without one the float outputs are lowered each in its
+            // own domain, which gives the same floats: float conversion and the observation's clip / scale are monotone,
+            // so float(min(a, b)) == min(float(a), float(b)).  (One corner differs: a NaN scan -- only injected NaN noise
+            // produces one on a finite pose -- stays NaN in the reference, whereas its observation value lm / lm can be
+            // lowered here when no scan output was asked for.)
+            if (best < INFINITY) {
+                if (io.scans_f64) {
+                    if (best < io.scans_f64[g]) {
+                        io.scans_f64[g] = best;
+                        if (io.scans_f32) io.scans_f32[g] = (float)best;
+                        if (a == 0 && io.obs) io.obs[(size_t)env * (B + 8) + i] = obs_lidar<false>(best, lm, 0.0f);
+                    }
+                } else {
+                    if (io.scans_f32) { const float nv = (float)best; if (nv < io.scans_f32[g]) io.scans_f32[g] = nv; }
+                    if (a == 0 && io.obs) {
+                        float* o = io.obs + (size_t)env * (B + 8) + i;
+                        const float nv = obs_lidar<false>(best, lm, 0.0f);
+                        if (nv < *o) *o = nv;
+                    }
+                }
             }
         }
         if (k + 1 < A) __syncthreads();   // the next round re-reads what this one lowered

@@ -65,7 +65,6 @@ struct StepScratch {
     double* head;       // [NA][4] per scan, for the lidar kernel: fixed-point map-frame start X, Y; wrapped theta index of beam 0
                         //          (laser_models.py:167-172); speed after the dynamics update (check_ttc_jit's vel)
     int32_t* ttc_hit;   // [NA] set by the lidar kernel
-    double* scan;       // [NA][B] noisy map scan, before the opponent ray-cast
     unsigned long long* lookups;  // [4] dt lookups, rays, longest ray, rays redone exactly (only with F110_FLAG_COUNT_LOOKUPS)
     double* stats;      // [F110_NUM_STATS]
     uint4* timeline;    // [num_units] or null: (start ns, end ns, longest ray, sm << 24 | queue position) of each unit in the

@@ -240,6 +240,39 @@ def test_tile_experiment_is_bit_identical_to_the_default_kernel():
     assert sum(int(t.sum()) for _, t, _ in runs['1'][1]) > 0     # episodes ended and restarted on the way
 
 
+@pytest.mark.parametrize('agents', [2, 4])
+def test_opponent_raycast_in_float_outputs_equals_the_fp64_path(agents):
+    """K3 lowers the beams that hit an opponent in the caller's own buffers (ray_cast_agents, base_classes.py:206-227).  With an
+    fp64 scan among the outputs that is the reference's min(scan, range) in fp64; without one the float outputs are lowered
+    each in its own domain.  Float conversion and the observation's clip / scale are monotone, so both give the same floats:
+    checked bit for bit over a rollout in which cars see, occlude and hit each other."""
+    _torch()
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim, workloads
+    N = 256
+    dt, res, origin = H.golden_map('Shanghai_map')
+    start = workloads.start_poses(N, agents)            # opponents 25 centerline rows (about 1.6 m) ahead of each other
+    rng = np.random.default_rng(11)
+    acts = rng.uniform([-0.3, 0.0], [0.3, 6.0], size=(150, N, agents, 2)).astype(np.float32)
+    traces = []
+    for outputs in (ALL_OUTPUTS, ('obs', 'scans_f32', 'reward', 'terminated')):
+        sim = BatchSim(N, agents, outputs=outputs, noise_std=0.01, seed=5)
+        sim.set_map_arrays(dt, res, origin)
+        out = sim.reset(start)
+        mask, tr = None, []
+        for t in range(150):
+            out = sim.step(acts[t], reset_mask=mask, reset_poses=start) if mask is not None else sim.step(acts[t])
+            torch.cuda.synchronize()
+            mask = out['terminated'].clone()
+            tr.append((out['obs'].cpu().numpy().copy(), out['scans_f32'].cpu().numpy().copy(), out['terminated'].cpu().numpy().copy()))
+        sim.close()
+        traces.append(tr)
+    for (o0, s0, t0), (o1, s1, t1) in zip(*traces):
+        assert np.array_equal(t0, t1) and np.array_equal(s0, s1) and np.array_equal(o0, o1)
+    # the opponent ahead is in view: the beams straight ahead of car 0 end on it, not on a wall tens of metres away
+    assert np.median(traces[1][0][1][:, 0, 520:560].min(axis=1)) < 2.5
+
+
 def test_c1_single_agent_sim_rollout():
     g = H.load('rollout_c1_single')
     be = make_gpu(1, 'Shanghai_map')
