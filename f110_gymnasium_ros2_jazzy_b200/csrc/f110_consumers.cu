@@ -17,118 +17,165 @@ int f110_set_error(int code, const char* msg);   // f110_capi.cu
 
 namespace {
 
-constexpr int GF_THREADS = 128;
+constexpr int GF_WARPS = 8;     // scans per CTA (one warp each); fewer when the scans are too long for that much shared memory
 
-struct RunSummary { int all_true, prefix, suffix, best_len, best_start; };
+// Summary of a stretch of the boolean sequence proc > threshold, in the form find_max_gap :21-38 needs: runs touching
+// the stretch's ends and the FIRST longest run closed inside it (metric end - start, as the reference's max(key=...)).
+// Summaries of adjacent stretches combine associatively, so a warp reduces 32 of them in five shuffles.
+struct RunSummary { int start, len, all_true, prefix, suffix, best_len, best_start; };
 
-__global__ void __launch_bounds__(GF_THREADS) gap_follow_kernel(const float* __restrict__ scans, long long scan_stride, int n,
-                                                                float* __restrict__ actions, long long action_stride,
-                                                                double angle_min, double angle_increment, float max_distance,
-                                                                int window_size, int bubble_radius, float threshold) {
-    extern __shared__ float sm[];
-    float* clipped = sm;           // [n]
-    float* proc = sm + n;          // [n]
-    __shared__ float s_wv[GF_THREADS / 32];
-    __shared__ int s_wi[GF_THREADS / 32];
-    __shared__ int s_closest;
-    __shared__ RunSummary s_run[GF_THREADS];
-    const int tid = threadIdx.x;
-    const float* scan = scans + (size_t)blockIdx.x * scan_stride;
-
-    // preprocess_lidar :3-12: mean of the clipped ranges over [i - w/2, i + w/2] cut at the ends
-    for (int i = tid; i < n; i += GF_THREADS) {
-        float v = scan[i];
-        v = v < 0.f ? 0.f : v;
-        v = v > max_distance ? max_distance : v;
-        clipped[i] = v;
+__device__ __forceinline__ RunSummary combine_runs(const RunSummary& L, const RunSummary& R) {
+    if (L.len == 0) return R;
+    if (R.len == 0) return L;
+    RunSummary o;
+    o.start = L.start;
+    o.len = L.len + R.len;
+    o.all_true = L.all_true && R.all_true;
+    o.prefix = L.all_true ? L.len + R.prefix : L.prefix;
+    o.suffix = R.all_true ? R.len + L.suffix : R.suffix;
+    o.best_len = L.best_len; o.best_start = L.best_start;
+    // the run across the boundary is closed on both sides only if neither stretch is all true
+    if (!L.all_true && !R.all_true && L.suffix + R.prefix > 0) {
+        const int m = L.suffix + R.prefix - 1;
+        if (m > o.best_len) { o.best_len = m; o.best_start = L.start + L.len - L.suffix; }
     }
-    __syncthreads();
-    const int half = window_size / 2;
+    if (R.best_len > o.best_len) { o.best_len = R.best_len; o.best_start = R.best_start; }
+    return o;
+}
+
+// the summary of `len` (1..32) consecutive beams starting at beam `base`, bit b of `w` = beam base + b is above the threshold
+__device__ __forceinline__ RunSummary word_runs(unsigned w, int len, int base) {
+    RunSummary r;
+    const unsigned full = len == 32 ? 0xffffffffu : (1u << len) - 1u;
+    w &= full;
+    r.start = base; r.len = len; r.best_len = -1; r.best_start = 0;
+    r.all_true = w == full;
+    if (r.all_true) { r.prefix = len; r.suffix = len; return r; }
+    r.prefix = __ffs((int)~w) - 1;                                 // ones from bit 0 up (~w != 0 here)
+    r.suffix = __clz((int)~(w << (32 - len)));                     // ones from bit len - 1 down
+    unsigned x = w;
+    if (r.prefix > 0) x &= ~((1u << r.prefix) - 1u);
+    if (r.suffix > 0) x &= (1u << (len - r.suffix)) - 1u;
+    while (x) {                                                    // the runs closed inside the word, lowest first
+        const int s0 = __ffs((int)x) - 1;
+        const unsigned y = ~(x >> s0);
+        const int run = y ? __ffs((int)y) - 1 : 32 - s0;
+        if (run - 1 > r.best_len) { r.best_len = run - 1; r.best_start = base + s0; }
+        x &= run + s0 >= 32 ? (1u << s0) - 1u : ~(((1u << run) - 1u) << s0);
+    }
+    return r;
+}
+
+// preprocess_lidar :3-12 for beam i: mean of the clipped ranges over [i - w/2, i + w/2] cut at the ends.
+// numpy sums fewer than 8 float32 elements sequentially; W > 0: the window size as a compile-time constant.
+template <int W>
+__device__ __forceinline__ float window_mean(const float* __restrict__ clipped, int i, int n, int window_size) {
+    const int half = (W > 0 ? W : window_size) / 2;
+    const int s = max(0, i - half), e = min(n - 1, i + half);
+    float acc = 0.f;
+    if (W > 0 && i - half >= 0 && i + half <= n - 1) {
+#pragma unroll
+        for (int k = 0; k < 2 * (W / 2) + 1; ++k) acc += clipped[i - half + k];
+    } else {
+        for (int k = s; k <= e; ++k) acc += clipped[k];
+    }
+    return __fdiv_rn(acc, (float)(e - s + 1));
+}
+
+// One WARP per scan, beam i = 32 k + lane in round k: every access coalesced, no barrier (round 1: a CTA per scan with five
+// barriers and a 128-step serial stitch by thread 0, 67 us per 8192 scans; timing under profiles/).
+template <int W>
+__global__ void __launch_bounds__(GF_WARPS * 32) gap_follow_kernel(const float* __restrict__ scans, long long scan_stride, int n,
+                                                                  long long num_scans, float* __restrict__ actions, long long action_stride,
+                                                                  double angle_min, double angle_increment, float max_distance,
+                                                                  int window_size, int bubble_radius, float threshold) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long scan_id = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+    if (scan_id >= num_scans) return;
+    const int groups = (n + 31) / 32;
+    float* clipped = sm + (size_t)wid * (n + groups);          // [n]
+    unsigned* words = reinterpret_cast<unsigned*>(clipped + n);   // [groups]: bit b of word k = beam 32 k + b is above the threshold
+    const float* scan = scans + (size_t)scan_id * scan_stride;
+
+    // the scan comes from DRAM (the lidar kernel wrote it with streaming stores): eight loads in flight per lane -- one
+    // at a time, a warp waited 34 DRAM round trips in a row and the kernel ran at a ninth of the memory's speed
+    constexpr int U = 8;
+    for (int base = 0; base < n; base += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + 32 * u + lane;
+            v[u] = i < n ? __ldcs(scan + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + 32 * u + lane;
+            float c = v[u] < 0.f ? 0.f : v[u];
+            c = c > max_distance ? max_distance : c;
+            if (i < n) clipped[i] = c;
+        }
+    }
+    __syncwarp();
+    // create_bubble :14-19: np.argmin = first minimum over the whole scan
     float best_v = INFINITY;
     int best_i = 0x7fffffff;
-    for (int i = tid; i < n; i += GF_THREADS) {
-        const int s = max(0, i - half), e = min(n - 1, i + half);
-        float acc = 0.f;
-        for (int k = s; k <= e; ++k) acc += clipped[k];          // numpy: sequential float32 sum for < 8 elements
-        const float m = __fdiv_rn(acc, (float)(e - s + 1));
-        proc[i] = m;
-        if (m < best_v) { best_v = m; best_i = i; }              // i increases: the first minimum of this thread
+    for (int i = lane; i < n; i += 32) {
+        const float m = window_mean<W>(clipped, i, n, window_size);
+        if (m < best_v) { best_v = m; best_i = i; }              // i increases: the first minimum of this lane
     }
-    // create_bubble :14-19: np.argmin = first minimum over the whole scan
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float v2 = __shfl_down_sync(0xffffffffu, best_v, o);
         const int i2 = __shfl_down_sync(0xffffffffu, best_i, o);
         if (v2 < best_v || (v2 == best_v && i2 < best_i)) { best_v = v2; best_i = i2; }
     }
-    if ((tid & 31) == 0) { s_wv[tid >> 5] = best_v; s_wi[tid >> 5] = best_i; }
-    __syncthreads();
-    if (tid == 0) {
-        float v = s_wv[0];
-        int idx = s_wi[0];
-        for (int w = 1; w < GF_THREADS / 32; ++w)
-            if (s_wv[w] < v || (s_wv[w] == v && s_wi[w] < idx)) { v = s_wv[w]; idx = s_wi[w]; }
-        s_closest = idx == 0x7fffffff ? 0 : idx;
+    int closest = __shfl_sync(0xffffffffu, best_i, 0);
+    closest = closest == 0x7fffffff ? 0 : closest;
+    const int b0 = max(closest - bubble_radius, 0), b1 = min(closest + bubble_radius, n - 1);
+    // find_max_gap :21-38: the mask, 32 beams per word (the bubble's beams hold 0)
+    for (int k = 0; k < groups; ++k) {
+        const int i = 32 * k + lane;
+        bool val = false;
+        if (i < n) val = ((i >= b0 && i <= b1) ? 0.f : window_mean<W>(clipped, i, n, window_size)) > threshold;
+        const unsigned w = __ballot_sync(0xffffffffu, val);
+        if (lane == 0) words[k] = w;
     }
-    __syncthreads();
-    {
-        const int s = max(s_closest - bubble_radius, 0), e = min(s_closest + bubble_radius, n - 1);
-        for (int i = s + tid; i <= e; i += GF_THREADS) proc[i] = 0.f;
+    __syncwarp();
+    // lane l summarises words [l * wc, (l + 1) * wc) in order, the warp joins the 32 summaries
+    const int wc = (groups + 31) / 32;
+    RunSummary r;
+    r.start = 0; r.len = 0; r.all_true = 1; r.prefix = 0; r.suffix = 0; r.best_len = -1; r.best_start = 0;
+    for (int j = lane * wc; j < min((lane + 1) * wc, groups); ++j)
+        r = combine_runs(r, word_runs(words[j], min(32, n - 32 * j), 32 * j));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RunSummary t;
+        t.start = __shfl_down_sync(0xffffffffu, r.start, o);
+        t.len = __shfl_down_sync(0xffffffffu, r.len, o);
+        t.all_true = __shfl_down_sync(0xffffffffu, r.all_true, o);
+        t.prefix = __shfl_down_sync(0xffffffffu, r.prefix, o);
+        t.suffix = __shfl_down_sync(0xffffffffu, r.suffix, o);
+        t.best_len = __shfl_down_sync(0xffffffffu, r.best_len, o);
+        t.best_start = __shfl_down_sync(0xffffffffu, r.best_start, o);
+        // lane l holds [l, l + o) and receives [l + o, l + 2 o): only lanes that are multiples of 2 o matter from here on
+        if ((lane & (2 * o - 1)) == 0) r = combine_runs(r, t);
     }
-    __syncthreads();
-
-    // find_max_gap :21-38: the FIRST longest run of proc > threshold.  Each thread summarises a contiguous chunk,
-    // thread 0 stitches the chunks in order.
-    const int chunk = (n + GF_THREADS - 1) / GF_THREADS;
-    {
-        const int c0 = min(tid * chunk, n), c1 = min(c0 + chunk, n);
-        RunSummary r;
-        r.all_true = 1; r.prefix = 0; r.suffix = 0; r.best_len = -1; r.best_start = 0;
-        int start = -1, seen_false = 0;
-        for (int i = c0; i < c1; ++i) {
-            const bool val = proc[i] > threshold;
-            if (val) {
-                if (start < 0) start = i;
-            } else {
-                if (start >= 0) {
-                    if (!seen_false && start == c0) r.prefix = i - c0;                 // run touching the chunk start
-                    else if (i - 1 - start > r.best_len) { r.best_len = i - 1 - start; r.best_start = start; }
-                    start = -1;
-                }
-                seen_false = 1;
-                r.all_true = 0;
-            }
-        }
-        if (start >= 0) {
-            if (r.all_true) r.prefix = c1 - c0;
-            r.suffix = c1 - start;
-        }
-        if (c0 == c1) { r.all_true = 1; r.prefix = 0; r.suffix = 0; }
-        s_run[tid] = r;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int best_s = 0, best_e = n - 1, best_len = -1, open = -1;
-        for (int t = 0; t < GF_THREADS; ++t) {
-            const int c0 = min(t * chunk, n), c1 = min(c0 + chunk, n);
-            if (c0 == c1) break;
-            const RunSummary r = s_run[t];
-            if (r.all_true) { if (open < 0) open = c0; continue; }
-            // a run entering from the left (or starting at c0) ends inside this chunk
-            if (open >= 0 || r.prefix > 0) {
-                const int st = open >= 0 ? open : c0;
-                const int en = c0 + r.prefix - 1;
-                if (en >= st && en - st > best_len) { best_len = en - st; best_s = st; best_e = en; }
-                open = -1;
-            }
+    if (lane == 0) {
+        // the runs of the whole scan in order: the one touching beam 0, the first longest closed one, the one touching
+        // beam n - 1; max(key = end - start) keeps the first of equals
+        int best_s = 0, best_e = n - 1, best_len = -1;
+        if (r.all_true) { best_len = n - 1; }
+        else {
+            if (r.prefix > 0) { best_len = r.prefix - 1; best_s = 0; best_e = r.prefix - 1; }
             if (r.best_len > best_len) { best_len = r.best_len; best_s = r.best_start; best_e = r.best_start + r.best_len; }
-            if (r.suffix > 0) open = c1 - r.suffix;
+            if (r.suffix > 0 && r.suffix - 1 > best_len) { best_len = r.suffix - 1; best_s = n - r.suffix; best_e = n - 1; }
         }
-        if (open >= 0 && n - 1 - open > best_len) { best_len = n - 1 - open; best_s = open; best_e = n - 1; }
         const int best = (best_s + best_e) / 2;                                   // find_best_point :40-41
         const double steering = angle_min + best * angle_increment;               // :49
         const double d10 = 10 * (3.141592653589793 / 180.0), d20 = 20 * (3.141592653589793 / 180.0);
         const double speed = fabs(steering) < d10 ? 2.5 : (fabs(steering) < d20 ? 2.0 : 1.5);
-        float* out = actions + (size_t)blockIdx.x * action_stride;
+        float* out = actions + (size_t)scan_id * action_stride;
         out[0] = (float)steering;
         out[1] = (float)speed;
     }
@@ -142,19 +189,14 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
     if (!scans || !actions || num_scans < 0 || num_beams < 1 || num_beams > 8192 || window_size < 1 || window_size > 15)
         return f110_set_error(F110_ERR_INVALID, "f110_gap_follow: need non-null buffers, 1 <= num_beams <= 8192, 1 <= window_size <= 15");
     if (num_scans == 0) return F110_OK;
-    const size_t gf_smem = 2 * sizeof(float) * (size_t)num_beams;
-    if (gf_smem > 48 * 1024) {   // above the default 48 KB a kernel has to opt in to its dynamic shared memory
-        static bool opted_in = false;
-        if (!opted_in) {
-            if (cudaFuncSetAttribute(gap_follow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess) {
-                cudaGetLastError();
-                return f110_set_error(F110_ERR_CUDA, "f110_gap_follow: cannot reserve 64 KB of shared memory");
-            }
-            opted_in = true;
-        }
-    }
-    gap_follow_kernel<<<(unsigned)num_scans, GF_THREADS, gf_smem, (cudaStream_t)stream>>>(
-        scans, scan_stride, num_beams, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
+    const size_t per_warp = sizeof(float) * ((size_t)num_beams + (size_t)(num_beams + 31) / 32);
+    int warps = (int)((48 * 1024) / per_warp);          // n <= 8192: a warp's scan always fits the 48 KB that need no opt-in
+    warps = warps > GF_WARPS ? GF_WARPS : (warps < 1 ? 1 : warps);
+    const size_t gf_smem = per_warp * warps;
+    void (*kernel)(const float*, long long, int, long long, float*, long long, double, double, float, int, int, float) =
+        window_size == 5 ? gap_follow_kernel<5> : gap_follow_kernel<0>;
+    kernel<<<(unsigned)((num_scans + warps - 1) / warps), warps * 32, gf_smem, (cudaStream_t)stream>>>(
+        scans, scan_stride, num_beams, num_scans, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
         bubble_radius, threshold);
     return cudaPeekAtLastError() == cudaSuccess ? F110_OK : f110_set_error(F110_ERR_CUDA, "f110_gap_follow: kernel launch failed");
 }

@@ -807,6 +807,27 @@ def test_gap_follow_kernel_bit_exact():
     torch.cuda.synchronize()
     refw = np.stack([gap_follow_action(s, angle_increment=np.pi / 8000) for s in wide]).astype(np.float32)
     assert np.array_equal(actw.cpu().numpy()[:, 1], refw)
+    # run structure: the kernel joins per-lane run summaries associatively -- blocky scans with runs of every length and
+    # position (ends on lane boundaries, equal-length runs where the first must win, all / none above the threshold), and
+    # beam counts around the warp size
+    rs = np.random.default_rng(21)
+    for nb in (31, 32, 33, 64, 100, 340, 1080, 1088):
+        blocky = np.zeros((200, nb), np.float32)
+        for row in blocky:
+            i = 0
+            while i < nb:
+                ln = int(rs.choice([1, 2, 3, 5, 8, 13, 33, 34, 35, 68, 100]))
+                row[i:i + ln] = rs.choice([0.0, 0.2, 0.6, 1.0, 3.0, 9.0])
+                i += ln
+        blocky[0] = 3.0; blocky[1] = 0.0; blocky[2] = 0.55
+        if nb >= 100:
+            blocky[3] = 0.0; blocky[3, 10:30] = 2.0; blocky[3, 60:80] = 2.0      # two equal runs far from the bubble's centre
+        tb = torch.from_numpy(np.stack([blocky, blocky], axis=1).copy()).cuda()
+        ab = torch.zeros((len(blocky), 2, 2), dtype=torch.float32, device='cuda')
+        gap_follow_actions(tb, ab, agent_idx=1, angle_increment=np.pi / nb)
+        torch.cuda.synchronize()
+        refb = np.stack([gap_follow_action(sc, angle_increment=np.pi / nb) for sc in blocky]).astype(np.float32)
+        assert np.array_equal(ab.cpu().numpy()[:, 1], refb), nb
 
 
 def test_consumers_survive_non_finite_inputs():
