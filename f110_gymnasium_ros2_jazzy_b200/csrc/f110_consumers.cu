@@ -66,19 +66,28 @@ __device__ __forceinline__ RunSummary word_runs(unsigned w, int len, int base) {
     return r;
 }
 
-// preprocess_lidar :3-12 for beam i: mean of the clipped ranges over [i - w/2, i + w/2] cut at the ends.
-// numpy sums fewer than 8 float32 elements sequentially; W > 0: the window size as a compile-time constant.
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// preprocess_lidar :3-12 for beam i: mean of the clipped ranges over [i - w/2, i + w/2] cut at the ends.  numpy sums fewer
+// than 8 float32 elements sequentially.  `clipped` is the array's 32-bit shared-memory address (formed once: indexed as a
+// C array, every access re-derived the shared window's base); W > 0 = the window size as a compile-time constant, whose
+// interior beams divide by a constant.
 template <int W>
-__device__ __forceinline__ float window_mean(const float* __restrict__ clipped, int i, int n, int window_size) {
+__device__ __forceinline__ float window_mean(unsigned clipped, int i, int n, int window_size) {
     const int half = (W > 0 ? W : window_size) / 2;
+    if (W > 0 && i >= half && i + half <= n - 1) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * (W / 2) + 1; ++k) acc += lds_f32(clipped + 4u * (unsigned)(i - half + k));
+        return __fdiv_rn(acc, (float)(2 * (W / 2) + 1));
+    }
     const int s = max(0, i - half), e = min(n - 1, i + half);
     float acc = 0.f;
-    if (W > 0 && i - half >= 0 && i + half <= n - 1) {
-#pragma unroll
-        for (int k = 0; k < 2 * (W / 2) + 1; ++k) acc += clipped[i - half + k];
-    } else {
-        for (int k = s; k <= e; ++k) acc += clipped[k];
-    }
+    for (int k = s; k <= e; ++k) acc += lds_f32(clipped + 4u * (unsigned)k);
     return __fdiv_rn(acc, (float)(e - s + 1));
 }
 
@@ -94,8 +103,9 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gap_follow_kernel(const float* 
     const long long scan_id = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
     if (scan_id >= num_scans) return;
     const int groups = (n + 31) / 32;
-    float* clipped = sm + (size_t)wid * (n + groups);          // [n]
-    unsigned* words = reinterpret_cast<unsigned*>(clipped + n);   // [groups]: bit b of word k = beam 32 k + b is above the threshold
+    float* clipped = sm + (size_t)wid * (2 * n + groups);      // [n]
+    float* proc = clipped + n;                                   // [n] the window means
+    unsigned* words = reinterpret_cast<unsigned*>(proc + n);     // [groups]: bit b of word k = beam 32 k + b is above the threshold
     const float* scan = scans + (size_t)scan_id * scan_stride;
 
     // the scan comes from DRAM (the lidar kernel wrote it with streaming stores): eight loads in flight per lane -- one
@@ -118,10 +128,12 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gap_follow_kernel(const float* 
     }
     __syncwarp();
     // create_bubble :14-19: np.argmin = first minimum over the whole scan
+    const unsigned clipped_addr = (unsigned)__cvta_generic_to_shared(clipped);
     float best_v = INFINITY;
     int best_i = 0x7fffffff;
     for (int i = lane; i < n; i += 32) {
-        const float m = window_mean<W>(clipped, i, n, window_size);
+        const float m = window_mean<W>(clipped_addr, i, n, window_size);
+        proc[i] = m;
         if (m < best_v) { best_v = m; best_i = i; }              // i increases: the first minimum of this lane
     }
 #pragma unroll
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gap_follow_kernel(const float* 
     for (int k = 0; k < groups; ++k) {
         const int i = 32 * k + lane;
         bool val = false;
-        if (i < n) val = ((i >= b0 && i <= b1) ? 0.f : window_mean<W>(clipped, i, n, window_size)) > threshold;
+        if (i < n) val = ((i >= b0 && i <= b1) ? 0.f : proc[i]) > threshold;      // own store: no sync needed
         const unsigned w = __ballot_sync(0xffffffffu, val);
         if (lane == 0) words[k] = w;
     }
@@ -189,12 +201,23 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
     if (!scans || !actions || num_scans < 0 || num_beams < 1 || num_beams > 8192 || window_size < 1 || window_size > 15)
         return f110_set_error(F110_ERR_INVALID, "f110_gap_follow: need non-null buffers, 1 <= num_beams <= 8192, 1 <= window_size <= 15");
     if (num_scans == 0) return F110_OK;
-    const size_t per_warp = sizeof(float) * ((size_t)num_beams + (size_t)(num_beams + 31) / 32);
-    int warps = (int)((48 * 1024) / per_warp);          // n <= 8192: a warp's scan always fits the 48 KB that need no opt-in
+    const size_t per_warp = sizeof(float) * (2 * (size_t)num_beams + (size_t)(num_beams + 31) / 32);
+    int warps = (int)((48 * 1024) / per_warp);          // stay within the 48 KB that need no opt-in where a scan allows it
     warps = warps > GF_WARPS ? GF_WARPS : (warps < 1 ? 1 : warps);
     const size_t gf_smem = per_warp * warps;
     void (*kernel)(const float*, long long, int, long long, float*, long long, double, double, float, int, int, float) =
         window_size == 5 ? gap_follow_kernel<5> : gap_follow_kernel<0>;
+    if (gf_smem > 48 * 1024) {   // one scan of more than 6 000 beams: the kernel has to opt in to its dynamic shared memory
+        static size_t opted_in[2] = {0, 0};
+        size_t& have = opted_in[window_size == 5 ? 0 : 1];
+        if (gf_smem > have) {
+            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf_smem) != cudaSuccess) {
+                cudaGetLastError();
+                return f110_set_error(F110_ERR_CUDA, "f110_gap_follow: cannot reserve the shared memory these scans need");
+            }
+            have = gf_smem;
+        }
+    }
     kernel<<<(unsigned)((num_scans + warps - 1) / warps), warps * 32, gf_smem, (cudaStream_t)stream>>>(
         scans, scan_stride, num_beams, num_scans, actions, action_stride, angle_min, angle_increment, max_distance, window_size,
         bubble_radius, threshold);
