@@ -421,10 +421,8 @@ __device__ __forceinline__ unsigned fast_div(unsigned n, FastDiv d) {
 template <bool FAST>
 __device__ __forceinline__ float obs_lidar(double range, float lm, float rcp) {
     float rf = (float)range;
-    if (rf != rf) rf = lm;
-    else if (isinf(rf)) rf = rf > 0 ? lm : 0.0f;
-    rf = rf < 0.0f ? 0.0f : rf;
-    rf = rf > lm ? lm : rf;
+    rf = rf != rf ? lm : rf;                 // nan -> lm; +inf -> lm and -inf -> 0 fall out of the clip
+    rf = fminf(fmaxf(rf, 0.0f), lm);
     if (FAST && (rf == 0.0f || rf >= 7.5e-37f)) {
         const float q0 = rf * rcp;
         return fmaf(fmaf(-q0, lm, rf), rcp, q0);
@@ -496,11 +494,15 @@ constexpr unsigned LIDAR_CHUNK = LIDAR_CHUNK_OVERRIDE;   // queue positions a wa
 // * The queue is one atomic counter (same-address atomics retire at about one per ns on this part: one fetch per unit
 //   costs 45 % at 32 768 envs); a fetch takes up to LIDAR_CHUNK positions at a time in the bulk of the light region, one
 //   near the ends, and is issued after the march of the chunk's last unit, so that its latency hides behind the epilogue.
-template <int FB, bool COUNT, bool DIRECT>
+// MODE 0: opponents follow (A >= 2); 1: single agent, the scan goes straight to the outputs; 2: single agent and the float32
+// observation is the only scan output, noise from the device stream -- the bulk throughput case (BASELINE configs 3 / 4),
+// without the unit's tests and address arithmetic for outputs that are not there.
+template <int FB, bool COUNT, int MODE>
 __global__ void __launch_bounds__(LIDAR_THREADS, LIDAR_MIN_BLOCKS)
 lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView m, const __grid_constant__ SimState st,
              const __grid_constant__ StepScratch sc, const __grid_constant__ F110StepIO io) {
     constexpr bool TUNED = FB != 0;
+    constexpr bool DIRECT = MODE != 0, OBS_ONLY = MODE == 2;
     cudaGridDependencySynchronize();   // PDL: everything below reads what the dynamics kernel (and the previous step) wrote
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nwarps = gridDim.x * (LIDAR_THREADS / 32);
@@ -668,7 +670,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // scan += noise, laser_models.py:450-452
                 const unsigned r = s * (unsigned)c.B + i;
                 double range = total_d;
-                if (io.noise) {
+                if (!OBS_ONLY && io.noise) {
                     range += io.noise[r];
                 } else if (c.noise_std > 0.0) {
                     // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
@@ -680,10 +682,10 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // beams that hit another car afterwards, in those same buffers.
                 // Streaming stores (evict-first): nothing in this kernel reads the outputs back, and at 32 768 envs the
                 // 142 MB of observations would otherwise push the map out of L2 (2.5 % of the kernel there).
-                if (io.scans_f64) __stcs(io.scans_f64 + r, range);
-                if (io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
+                if (!OBS_ONLY && io.scans_f64) __stcs(io.scans_f64 + r, range);
+                if (!OBS_ONLY && io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
                 if (DIRECT) {
-                    if (io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
+                    if (OBS_ONLY || io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 } else {
                     if (io.obs && s == env * (unsigned)c.A)
                         __stcs(io.obs + (size_t)env * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
@@ -1495,19 +1497,19 @@ cudaError_t launch_dynamics(const SimConst& c, const MapView& m, const SimState&
 
 typedef void (*LidarKernel)(SimConst, MapView, SimState, StepScratch, F110StepIO);
 
-template <bool DIRECT>
+template <int MODE>
 static LidarKernel lidar_variant_t(int fb, bool count) {
     switch (fb) {
-        case 19: return count ? lidar_kernel<19, true, DIRECT> : lidar_kernel<19, false, DIRECT>;
-        case 20: return count ? lidar_kernel<20, true, DIRECT> : lidar_kernel<20, false, DIRECT>;
-        case 21: return count ? lidar_kernel<21, true, DIRECT> : lidar_kernel<21, false, DIRECT>;
-        case 22: return count ? lidar_kernel<22, true, DIRECT> : lidar_kernel<22, false, DIRECT>;
-        default: return count ? lidar_kernel<0, true, DIRECT> : lidar_kernel<0, false, DIRECT>;
+        case 19: return count ? lidar_kernel<19, true, MODE> : lidar_kernel<19, false, MODE>;
+        case 20: return count ? lidar_kernel<20, true, MODE> : lidar_kernel<20, false, MODE>;
+        case 21: return count ? lidar_kernel<21, true, MODE> : lidar_kernel<21, false, MODE>;
+        case 22: return count ? lidar_kernel<22, true, MODE> : lidar_kernel<22, false, MODE>;
+        default: return count ? lidar_kernel<0, true, MODE> : lidar_kernel<0, false, MODE>;
     }
 }
-// fb = the map's fraction bits when the TUNED variant applies, else 0
-static LidarKernel lidar_variant(int fb, bool count, bool direct) {
-    return direct ? lidar_variant_t<true>(fb, count) : lidar_variant_t<false>(fb, count);
+// fb = the map's fraction bits when the TUNED variant applies, else 0; mode as in lidar_kernel
+static LidarKernel lidar_variant(int fb, bool count, int mode) {
+    return mode == 2 ? lidar_variant_t<2>(fb, count) : mode == 1 ? lidar_variant_t<1>(fb, count) : lidar_variant_t<0>(fb, count);
 }
 
 // CTAs of the lidar kernel that are resident at once on the current device (one wave of persistent warps)
@@ -1515,7 +1517,7 @@ int lidar_resident_blocks(bool single_agent) {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lidar_variant(21, false, single_agent), LIDAR_THREADS, 0) != cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lidar_variant(21, false, single_agent ? 1 : 0), LIDAR_THREADS, 0) != cudaSuccess)
         return -1;
     return sms * per_sm;
 }
@@ -1539,7 +1541,8 @@ cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st
     // one wave of persistent warps, or fewer when there are not that many units
     const unsigned want = (sc.num_units + LIDAR_THREADS / 32 - 1) / (LIDAR_THREADS / 32);
     const unsigned blocks = want < (unsigned)resident_blocks ? want : (unsigned)resident_blocks;
-    return launch_pdl(lidar_variant(tuned ? (int)m.fx_bits : 0, count_lookups, c.A == 1), dim3(blocks ? blocks : 1u), dim3(LIDAR_THREADS), 0,
+    const int mode = c.A != 1 ? 0 : (io.obs && !io.noise && !io.scans_f64 && !io.scans_f32) ? 2 : 1;
+    return launch_pdl(lidar_variant(tuned ? (int)m.fx_bits : 0, count_lookups, mode), dim3(blocks ? blocks : 1u), dim3(LIDAR_THREADS), 0,
                       s, c, m, st, sc, io);
 }
 
