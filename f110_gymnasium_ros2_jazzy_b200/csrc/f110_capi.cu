@@ -284,6 +284,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     c.beam_cos = t; t += B;
     c.side_dist = t; t += B;
     c.beam_tt = sim->d_lidar_tables;
+    c.ttc_side_max = INFINITY; c.ttc_cos_max = INFINITY;
     c.dir_fx = sim->d_lidar_tables + B;
     sim->h_sines.assign(cfg->theta_dis, 0.0); sim->h_cosines.assign(cfg->theta_dis, 1.0);
 
@@ -444,6 +445,15 @@ int f110_set_beam_tables(F110Sim* sim, const double* scan_angles, const double* 
     std::vector<double2> bt(sim->cfg.num_beams);
     for (int i = 0; i < sim->cfg.num_beams; ++i) { bt[i].x = beam_cosines[i]; bt[i].y = side_distances[i]; }
     CUDA_TRY(cudaMemcpy(const_cast<double2*>(sim->c.beam_tt), bt.data(), bt.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    // the scan-wide iTTC prefilter of the dynamics kernel: bounds over the tables (non-finite entries switch it off)
+    double side_max = 0.0, cos_max = 0.0;
+    for (int i = 0; i < sim->cfg.num_beams; ++i) {
+        const double sd = side_distances[i], bc = fabs(beam_cosines[i]);
+        side_max = sd > side_max || !(sd == sd) ? (sd == sd ? sd : INFINITY) : side_max;
+        cos_max = bc > cos_max || !(bc == bc) ? (bc == bc ? bc : INFINITY) : cos_max;
+    }
+    sim->c.ttc_side_max = side_max;
+    sim->c.ttc_cos_max = cos_max;
     return F110_OK;
 }
 

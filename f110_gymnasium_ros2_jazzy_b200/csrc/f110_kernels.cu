@@ -280,7 +280,11 @@ __global__ void __launch_bounds__(128) dynamics_kernel(SimConst c, MapView m, Si
     head.x = (x_trans * m.oc + y_trans * m.os) * m.inv_fx + m.fx_off;
     head.y = (-x_trans * m.os + y_trans * m.oc) * m.inv_fx + m.fx_off;
     head.z = ti;
-    head.w = x[3];
+    // iTTC prefilter for the whole scan (check_ttc_jit, laser_models.py:205-213): ttc = (range - side) / (v cos) lies in
+    // [0, thresh) only if range - side <= thresh |v cos|, so a range above max(side) + 2.5 thresh |v| max|cos| (the margin
+    // swallows every rounding) cannot hit on ANY beam, and neither can a car at rest (the reference tests vel != 0 first).
+    // NaN compares false in the lidar kernel's `range > limit` and falls through to the exact test.
+    head.w = x[3] != 0.0 ? c.ttc_side_max + 2.5 * c.ttc_thresh * fabs(x[3]) * c.ttc_cos_max : -INFINITY;
     reinterpret_cast<double4*>(sc.head)[s] = head;
     sc.ttc_hit[s] = 0;
     }   // run
@@ -567,8 +571,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             const unsigned env = DIRECT ? s : fast_div(s, c.div_A);
             live = i < (unsigned)c.B && !(io.active_mask && !io.active_mask[env]);
             const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;      // the dead lanes of a scan's last unit shadow its last beam
-            const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; speed
-            const double2 bt = __ldg(c.beam_tt + ic);                            // beam cosine, side distance (check_ttc_jit)
+            const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; iTTC limit
             const unsigned stepc = st.step_count[env];
             // beam direction: closed form of the reference's running sum theta_index += increment with wrap
             // (laser_models.py:174-184).  The running sum differs from the closed form by < 1.3e-10 after
@@ -588,11 +591,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             // memory safety only: a NaN yaw (a car poisoned by a NaN command) converts to a NEGATIVE index on this hardware
             ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
             const double2 dir = __ldg(c.dir_fx + ti);
-            // iTTC prefilter (check_ttc_jit, laser_models.py:205-213): ttc = (range - side) / (v cos) lies in [0, thresh) only
-            // if range - side <= thresh |v cos|; a range above ttc_lim = side + 2.5 thresh |v cos| (the margin swallows every
-            // rounding here) cannot hit, and neither can a car at rest (the reference tests vel != 0 first).  NaNs compare
-            // false and fall through to the exact test.
-            const double ttc_lim = head.w != 0.0 ? bt.y + 2.5 * c.ttc_thresh * fabs(head.w * bt.x) : -INFINITY;
+            const double ttc_lim = head.w;      // iTTC prefilter of the scan, formed by the dynamics kernel
 
             // ---- the march
             double X = head.x, Y = head.y, total_d = 0.0, d = 0.0;
@@ -693,8 +692,8 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // check_ttc_jit (any-reduction; the reference's early break is irrelevant)
                 if (!(range > ttc_lim)) {
                     // (rare: re-read rather than keep four registers alive across the march)
-                    const double2 bt2 = __ldg(c.beam_tt + i);
-                    const double ttc = (range - bt2.y) / (sc.head[4u * s + 3u] * bt2.x);
+                    const double2 bt2 = __ldg(c.beam_tt + i);        // beam cosine, side distance
+                    const double ttc = (range - bt2.y) / (st.x[3][s] * bt2.x);
                     if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
                 }
             }
@@ -794,7 +793,7 @@ lidar_tile_kernel(const __grid_constant__ SimConst c, const __grid_constant__ Ma
     __syncthreads();
     unsigned phase = 0;
     for (unsigned s = blockIdx.x; s < (unsigned)c.NA; s += gridDim.x) {
-        const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; speed
+        const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; iTTC limit
         const unsigned hx = __double2uint_rz(head.x), hy = __double2uint_rz(head.y);
         int c0 = (int)(hx >> FB) - TILE_T, r0 = (int)(hy >> FB) - TILE_T;
         c0 = c0 < 0 ? 0 : (c0 > pitch - TILE_COLS ? pitch - TILE_COLS : c0);
@@ -826,7 +825,6 @@ lidar_tile_kernel(const __grid_constant__ SimConst c, const __grid_constant__ Ma
             const unsigned i = k * 32u + lane;
             const bool live = i < (unsigned)c.B && active;
             const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;
-            const double2 bt = __ldg(c.beam_tt + ic);
             // beam direction: as in lidar_kernel (laser_models.py:174-184)
             const double td = (double)c.theta_dis;
             double t = head.z + (double)ic * c.theta_inc;
@@ -841,7 +839,7 @@ lidar_tile_kernel(const __grid_constant__ SimConst c, const __grid_constant__ Ma
             int ti = (int)t;
             ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
             const double2 dir = __ldg(c.dir_fx + ti);
-            const double ttc_lim = head.w != 0.0 ? bt.y + 2.5 * c.ttc_thresh * fabs(head.w * bt.x) : -INFINITY;
+            const double ttc_lim = head.w;
 
             double X = head.x, Y = head.y, total_d = 0.0, d = 0.0;
             bool decided = true;
@@ -894,7 +892,8 @@ lidar_tile_kernel(const __grid_constant__ SimConst c, const __grid_constant__ Ma
                 if (io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
                 if (io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<true>(range, c.lidar_max, c.obs_rcp));
                 if (!(range > ttc_lim)) {
-                    const double ttc = (range - bt.y) / (head.w * bt.x);
+                    const double2 bt = __ldg(c.beam_tt + i);
+                    const double ttc = (range - bt.y) / (st.x[3][s] * bt.x);
                     if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
                 }
             }

@@ -63,7 +63,7 @@ struct StepScratch {
     double* scan_y;
     double* pre_yaw;    // [NA] yaw after dynamics, BEFORE iTTC zeroing (Simulator.agent_poses, :587)
     double* head;       // [NA][4] per scan, for the lidar kernel: fixed-point map-frame start X, Y; wrapped theta index of beam 0
-                        //          (laser_models.py:167-172); speed after the dynamics update (check_ttc_jit's vel)
+                        //          (laser_models.py:167-172); the range above which no beam of the scan can trip the iTTC test
     int32_t* ttc_hit;   // [NA] set by the lidar kernel
     unsigned long long* lookups;  // [4] dt lookups, rays, longest ray, rays redone exactly (only with F110_FLAG_COUNT_LOOKUPS)
     double* stats;      // [F110_NUM_STATS]
@@ -106,6 +106,7 @@ struct SimConst {
     const double* beam_cos;    // [B]
     const double* side_dist;   // [B]
     const double2* beam_tt;    // [B] (beam_cos, side_dist) interleaved for the lidar kernel
+    double ttc_side_max, ttc_cos_max;   // max side_dist, max |beam_cos| (+inf until the beam tables are set: nothing is pre-filtered)
     const double2* dir_fx;     // [theta_dis] table direction k rotated into the map frame and scaled to fixed point:
                                //   ((cos*oc + sin*os) * inv_fx, (-cos*os + sin*oc) * inv_fy); rebuilt by set_map / set_tables
 };
