@@ -500,7 +500,7 @@ constexpr unsigned LIDAR_CHUNK = LIDAR_CHUNK_OVERRIDE;   // queue positions a wa
 //   near the ends, and is issued after the march of the chunk's last unit, so that its latency hides behind the epilogue.
 // MODE 0: opponents follow (A >= 2); 1: single agent, the scan goes straight to the outputs; 2: single agent and the float32
 // observation is the only scan output, noise from the device stream -- the bulk throughput case (BASELINE configs 3 / 4),
-// without the unit's tests and address arithmetic for outputs that are not there.
+// no mask of active envs -- without the unit's tests and address arithmetic for what is not there.
 template <int FB, bool COUNT, int MODE>
 __global__ void __launch_bounds__(LIDAR_THREADS, LIDAR_MIN_BLOCKS)
 lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView m, const __grid_constant__ SimState st,
@@ -569,7 +569,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             const unsigned s = fast_div(unit, c.div_ups);
             const unsigned i = (unit - s * c.ups) * 32u + lane;
             const unsigned env = DIRECT ? s : fast_div(s, c.div_A);
-            live = i < (unsigned)c.B && !(io.active_mask && !io.active_mask[env]);
+            live = i < (unsigned)c.B && (OBS_ONLY || !(io.active_mask && !io.active_mask[env]));
             const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;      // the dead lanes of a scan's last unit shadow its last beam
             const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; iTTC limit
             const unsigned stepc = st.step_count[env];
@@ -684,10 +684,10 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 if (!OBS_ONLY && io.scans_f64) __stcs(io.scans_f64 + r, range);
                 if (!OBS_ONLY && io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
                 if (DIRECT) {
-                    if (OBS_ONLY || io.obs) __stcs(io.obs + (size_t)s * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
+                    if (OBS_ONLY || io.obs) __stcs(io.obs + (s * (unsigned)(c.B + 8) + i), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));   // < 2^32 elements
                 } else {
                     if (io.obs && s == env * (unsigned)c.A)
-                        __stcs(io.obs + (size_t)env * (c.B + 8) + i, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
+                        __stcs(io.obs + (env * (unsigned)(c.B + 8) + i), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 }
                 // check_ttc_jit (any-reduction; the reference's early break is irrelevant)
                 if (!(range > ttc_lim)) {
@@ -1540,7 +1540,7 @@ cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st
     // one wave of persistent warps, or fewer when there are not that many units
     const unsigned want = (sc.num_units + LIDAR_THREADS / 32 - 1) / (LIDAR_THREADS / 32);
     const unsigned blocks = want < (unsigned)resident_blocks ? want : (unsigned)resident_blocks;
-    const int mode = c.A != 1 ? 0 : (io.obs && !io.noise && !io.scans_f64 && !io.scans_f32) ? 2 : 1;
+    const int mode = c.A != 1 ? 0 : (io.obs && !io.noise && !io.scans_f64 && !io.scans_f32 && !io.active_mask) ? 2 : 1;
     return launch_pdl(lidar_variant(tuned ? (int)m.fx_bits : 0, count_lookups, mode), dim3(blocks ? blocks : 1u), dim3(LIDAR_THREADS), 0,
                       s, c, m, st, sc, io);
 }
