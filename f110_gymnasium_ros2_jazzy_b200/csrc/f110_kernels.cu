@@ -499,14 +499,15 @@ constexpr unsigned LIDAR_CHUNK = LIDAR_CHUNK_OVERRIDE;   // queue positions a wa
 //   costs 45 % at 32 768 envs); a fetch takes up to LIDAR_CHUNK positions at a time in the bulk of the light region, one
 //   near the ends, and is issued after the march of the chunk's last unit, so that its latency hides behind the epilogue.
 // MODE 0: opponents follow (A >= 2); 1: single agent, the scan goes straight to the outputs; 2: single agent and the float32
-// observation is the only scan output, noise from the device stream -- the bulk throughput case (BASELINE configs 3 / 4),
-// no mask of active envs -- without the unit's tests and address arithmetic for what is not there.
+// observation is the only scan output, noise from the device stream, no mask of active envs -- the bulk throughput case
+// (BASELINE configs 3 / 4) -- without the unit's tests and address arithmetic for what is not there; 3: opponents, likewise
+// lean (device noise, no fp64 scan output, no mask: BASELINE config 5).
 template <int FB, bool COUNT, int MODE>
 __global__ void __launch_bounds__(LIDAR_THREADS, LIDAR_MIN_BLOCKS)
 lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView m, const __grid_constant__ SimState st,
              const __grid_constant__ StepScratch sc, const __grid_constant__ F110StepIO io) {
     constexpr bool TUNED = FB != 0;
-    constexpr bool DIRECT = MODE != 0, OBS_ONLY = MODE == 2;
+    constexpr bool DIRECT = MODE == 1 || MODE == 2, OBS_ONLY = MODE == 2, LEAN = MODE >= 2;
     cudaGridDependencySynchronize();   // PDL: everything below reads what the dynamics kernel (and the previous step) wrote
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nwarps = gridDim.x * (LIDAR_THREADS / 32);
@@ -569,7 +570,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             const unsigned s = fast_div(unit, c.div_ups);
             const unsigned i = (unit - s * c.ups) * 32u + lane;
             const unsigned env = DIRECT ? s : fast_div(s, c.div_A);
-            live = i < (unsigned)c.B && (OBS_ONLY || !(io.active_mask && !io.active_mask[env]));
+            live = i < (unsigned)c.B && (LEAN || !(io.active_mask && !io.active_mask[env]));
             const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;      // the dead lanes of a scan's last unit shadow its last beam
             const double4 head = reinterpret_cast<const double4*>(sc.head)[s];   // fixed-point start X, Y; theta index of beam 0; iTTC limit
             const unsigned stepc = st.step_count[env];
@@ -669,7 +670,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // scan += noise, laser_models.py:450-452
                 const unsigned r = s * (unsigned)c.B + i;
                 double range = total_d;
-                if (!OBS_ONLY && io.noise) {
+                if (!LEAN && io.noise) {
                     range += io.noise[r];
                 } else if (c.noise_std > 0.0) {
                     // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
@@ -681,7 +682,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // beams that hit another car afterwards, in those same buffers.
                 // Streaming stores (evict-first): nothing in this kernel reads the outputs back, and at 32 768 envs the
                 // 142 MB of observations would otherwise push the map out of L2 (2.5 % of the kernel there).
-                if (!OBS_ONLY && io.scans_f64) __stcs(io.scans_f64 + r, range);
+                if (!LEAN && io.scans_f64) __stcs(io.scans_f64 + r, range);
                 if (!OBS_ONLY && io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
                 if (DIRECT) {
                     if (OBS_ONLY || io.obs) __stcs(io.obs + (s * (unsigned)(c.B + 8) + i), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));   // < 2^32 elements
@@ -1508,7 +1509,8 @@ static LidarKernel lidar_variant_t(int fb, bool count) {
 }
 // fb = the map's fraction bits when the TUNED variant applies, else 0; mode as in lidar_kernel
 static LidarKernel lidar_variant(int fb, bool count, int mode) {
-    return mode == 2 ? lidar_variant_t<2>(fb, count) : mode == 1 ? lidar_variant_t<1>(fb, count) : lidar_variant_t<0>(fb, count);
+    return mode == 3 ? lidar_variant_t<3>(fb, count) : mode == 2 ? lidar_variant_t<2>(fb, count) :
+           mode == 1 ? lidar_variant_t<1>(fb, count) : lidar_variant_t<0>(fb, count);
 }
 
 // CTAs of the lidar kernel that are resident at once on the current device (one wave of persistent warps)
@@ -1540,7 +1542,8 @@ cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st
     // one wave of persistent warps, or fewer when there are not that many units
     const unsigned want = (sc.num_units + LIDAR_THREADS / 32 - 1) / (LIDAR_THREADS / 32);
     const unsigned blocks = want < (unsigned)resident_blocks ? want : (unsigned)resident_blocks;
-    const int mode = c.A != 1 ? 0 : (io.obs && !io.noise && !io.scans_f64 && !io.scans_f32 && !io.active_mask) ? 2 : 1;
+    const bool lean = !io.noise && !io.scans_f64 && !io.active_mask;
+    const int mode = c.A != 1 ? (lean ? 3 : 0) : (lean && io.obs && !io.scans_f32) ? 2 : 1;
     return launch_pdl(lidar_variant(tuned ? (int)m.fx_bits : 0, count_lookups, mode), dim3(blocks ? blocks : 1u), dim3(LIDAR_THREADS), 0,
                       s, c, m, st, sc, io);
 }

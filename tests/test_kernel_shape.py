@@ -34,7 +34,7 @@ def _lidar_variants(fns):
 
 def test_lidar_kernel_register_budget():
     fns = _lidar_variants(_functions(["-res-usage"]))
-    assert len(fns) == 30                                       # fraction bits {generic, 19..22} x COUNT x MODE
+    assert len(fns) == 40                                       # fraction bits {generic, 19..22} x COUNT x MODE
     for name, lines in fns.items():
         text = " ".join(lines)
         reg = int(re.search(r"REG:(\d+)", text).group(1))
@@ -45,7 +45,7 @@ def test_lidar_kernel_register_budget():
 
 def test_lidar_hot_loop_has_no_call_and_no_local_memory():
     fns = _lidar_variants(_functions(["-sass"]))
-    assert len(fns) == 30
+    assert len(fns) == 40
     for name, lines in fns.items():
         ins = []
         for line in lines:
