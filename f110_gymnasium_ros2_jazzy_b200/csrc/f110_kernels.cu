@@ -454,6 +454,9 @@ constexpr int LIDAR_THREADS = LIDAR_THREADS_OVERRIDE;
 #ifndef LIDAR_CHUNK_OVERRIDE
 #define LIDAR_CHUNK_OVERRIDE 4
 #endif
+#ifndef LIDAR_LIST2_TAKE
+#define LIDAR_LIST2_TAKE 2u    // positions per fetch in the third (lightest) heavy list (1 in the two heavier ones)
+#endif
 #ifndef LIDAR_MIN_TAKE
 #define LIDAR_MIN_TAKE 2u     // positions per fetch in the last stretch of the light region (see `fetch`)
 #endif
@@ -554,7 +557,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
     // one counter serves (about 1.4 fetches per ns) -- two at a time costs 1.6 us of balance and was 3 % faster at 4096 envs.
     auto fetch = [&](unsigned at) {
         take = (npos - at) / (2u * nwarps);
-        take = at < n2 ? 1u : take < LIDAR_MIN_TAKE ? LIDAR_MIN_TAKE : (take > (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) ? (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) : take);
+        take = at < n1 ? 1u : at < n2 ? LIDAR_LIST2_TAKE : take < LIDAR_MIN_TAKE ? LIDAR_MIN_TAKE : (take > (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) ? (sc.ordered ? LIDAR_CHUNK : 2u * LIDAR_CHUNK) : take);
         if (lane == 0) f = atomicAdd(qpos, take) + nwarps;
     };
     unsigned unit; bool skip;
