@@ -240,6 +240,37 @@ def test_tile_experiment_is_bit_identical_to_the_default_kernel():
     assert sum(int(t.sum()) for _, t, _ in runs['1'][1]) > 0     # episodes ended and restarted on the way
 
 
+def test_lean_lidar_variants_equal_the_general_one():
+    """The lidar kernel has variants without the tests and address arithmetic for outputs that were not asked for (single
+    agent: float32 observation only; opponents: no fp64 scan; both: device noise, no env mask).  Same seed, same actions:
+    the observation, reward and terminated flags equal those of the general variant (ALL_OUTPUTS) bit for bit."""
+    _torch()
+    import torch
+    from f110_gymnasium_ros2_jazzy_b200 import ALL_OUTPUTS, BatchSim, workloads
+    dt, res, origin = H.golden_map('Shanghai_map')
+    rng = np.random.default_rng(13)
+    for agents, lean in ((1, ('obs', 'reward', 'terminated')), (2, ('obs', 'scans_f32', 'reward', 'terminated'))):
+        N = 300
+        start = workloads.start_poses(N, agents)
+        acts = rng.uniform([-0.4189, 0.0], [0.4189, 10.0], size=(120, N, agents, 2)).astype(np.float32)
+        traces = []
+        for outputs in (ALL_OUTPUTS, lean):
+            sim = BatchSim(N, agents, outputs=outputs, noise_std=0.01, seed=17)
+            sim.set_map_arrays(dt, res, origin)
+            out = sim.reset(start)
+            mask, tr = None, []
+            for t in range(120):
+                out = sim.step(acts[t], reset_mask=mask, reset_poses=start) if mask is not None else sim.step(acts[t])
+                torch.cuda.synchronize()
+                mask = out['terminated'].clone()
+                tr.append((out['obs'].cpu().numpy().copy(), out['terminated'].cpu().numpy().copy()))
+            sim.close()
+            traces.append(tr)
+        for (o0, t0), (o1, t1) in zip(*traces):
+            assert np.array_equal(t0, t1) and np.array_equal(o0, o1), agents
+        assert sum(int(t.sum()) for _, t in traces[1]) > 0
+
+
 @pytest.mark.parametrize('agents', [2, 4])
 def test_opponent_raycast_in_float_outputs_equals_the_fp64_path(agents):
     """K3 lowers the beams that hit an opponent in the caller's own buffers (ray_cast_agents, base_classes.py:206-227).  With an
