@@ -596,6 +596,10 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             ti = (unsigned)ti < (unsigned)c.theta_dis ? ti : c.theta_dis - 1;
             const double2 dir = __ldg(c.dir_fx + ti);
             const double ttc_lim = head.w;      // iTTC prefilter of the scan, formed by the dynamics kernel
+            // the ray's id: its element of the observation when the scan goes there, and the counter of its noise.  The one
+            // thing about the ray's place that the common path still needs after the march (< 2^32: f110_create bounds
+            // NA * B by 2^31 and B >= 32).
+            const unsigned rid = s * (unsigned)(c.B + 8) + i;
 
             // ---- the march
             double X = head.x, Y = head.y, total_d = 0.0, d = 0.0;
@@ -671,14 +675,14 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
 
             if (live) {
                 // scan += noise, laser_models.py:450-452
-                const unsigned r = s * (unsigned)c.B + i;
+                const unsigned r = OBS_ONLY ? 0u : rid - 8u * s;      // s * B + i: the ray's element of the scan outputs
                 double range = total_d;
                 if (!LEAN && io.noise) {
                     range += io.noise[r];
                 } else if (c.noise_std > 0.0) {
                     // counter = (ray id, steps since the env's reset): like the reference's generator, which is re-seeded by
                     // reset (base_classes.py:204), the stream restarts with every episode; unlike it, every ray has its own
-                    const uint2 bits = philox2x32_10(make_uint2(r, stepc), c.philox_key);
+                    const uint2 bits = philox2x32_10(make_uint2(rid, stepc), c.philox_key);
                     range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
                 }
                 // The scan goes straight to the caller's buffers.  With opponents (A >= 2) the post kernel lowers the few
@@ -688,17 +692,18 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 if (!LEAN && io.scans_f64) __stcs(io.scans_f64 + r, range);
                 if (!OBS_ONLY && io.scans_f32) __stcs(io.scans_f32 + r, (float)range);
                 if (DIRECT) {
-                    if (OBS_ONLY || io.obs) __stcs(io.obs + (s * (unsigned)(c.B + 8) + i), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));   // < 2^32 elements
+                    if (OBS_ONLY || io.obs) __stcs(io.obs + rid, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 } else {
                     if (io.obs && s == env * (unsigned)c.A)
                         __stcs(io.obs + (env * (unsigned)(c.B + 8) + i), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
                 }
                 // check_ttc_jit (any-reduction; the reference's early break is irrelevant)
                 if (!(range > ttc_lim)) {
-                    // (rare: re-read rather than keep four registers alive across the march)
-                    const double2 bt2 = __ldg(c.beam_tt + i);        // beam cosine, side distance
-                    const double ttc = (range - bt2.y) / (st.x[3][s] * bt2.x);
-                    if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s] = 1;
+                    // (rare: re-derive the ray's place and re-read its table rather than keep them alive across the march)
+                    const unsigned s2 = fast_div(unit, c.div_ups), i2 = (unit - s2 * c.ups) * 32u + lane;
+                    const double2 bt2 = __ldg(c.beam_tt + i2);       // beam cosine, side distance
+                    const double ttc = (range - bt2.y) / (st.x[3][s2] * bt2.x);
+                    if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s2] = 1;
                 }
             }
             // ---- history for the next step's launch order.  The class goes to the unit AND its two neighbours in the scan: a
@@ -709,7 +714,7 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
             if (lane == 3u && sc.ordered) cur_cls[unit] = done;
             if (wmax >= HEAVY_T2 && lane < 3u && sc.ordered) {
                 const unsigned b = wmax >= HEAVY_T0 ? 0u : (wmax >= HEAVY_T1 ? 1u : 2u);
-                const unsigned k = unit - s * c.ups;
+                const unsigned k = unit - fast_div(unit, c.div_ups) * c.ups;
                 const bool in_scan = lane == 1u || (lane == 0u ? k > 0u : k + 1u < c.ups);
                 if (in_scan) {
                     const unsigned u = unit + lane - 1u;
@@ -884,12 +889,12 @@ lidar_tile_kernel(const __grid_constant__ SimConst c, const __grid_constant__ Ma
             if (live && (!decided || d < 0.0)) total_d = trace_ray_exact(m, c, sc, s, ti).x;
             if (total_d > c.max_range) total_d = c.max_range;
             if (live) {
-                const unsigned r = s * (unsigned)c.B + i;
+                const unsigned r = s * (unsigned)c.B + i, rid = s * (unsigned)(c.B + 8) + i;   // as in lidar_kernel
                 double range = total_d;
                 if (io.noise) {
                     range += io.noise[r];
                 } else if (c.noise_std > 0.0) {
-                    const uint2 bits = philox2x32_10(make_uint2(r, stepc), c.philox_key);
+                    const uint2 bits = philox2x32_10(make_uint2(rid, stepc), c.philox_key);
                     range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
                 }
                 if (io.scans_f64) __stcs(io.scans_f64 + r, range);
