@@ -208,8 +208,10 @@ extern "C" int f110_gap_follow(const float* scans, int64_t num_scans, int64_t sc
     void (*kernel)(const float*, long long, int, long long, float*, long long, double, double, float, int, int, float) =
         window_size == 5 ? gap_follow_kernel<5> : gap_follow_kernel<0>;
     if (gf_smem > 48 * 1024) {   // one scan of more than 6 000 beams: the kernel has to opt in to its dynamic shared memory
-        static size_t opted_in[2] = {0, 0};
-        size_t& have = opted_in[window_size == 5 ? 0 : 1];
+        static size_t opted_in[64][2] = {};      // per device (the attribute is a per-device property of the function)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& have = opted_in[dev & 63][window_size == 5 ? 0 : 1];
         if (gf_smem > have) {
             if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gf_smem) != cudaSuccess) {
                 cudaGetLastError();
