@@ -132,7 +132,12 @@ typedef struct F110StepIO {
 const char* f110_last_error(void);
 int f110_abi_version(void);
 
-/* params: F110_NUM_PARAMS doubles applied to every agent (Simulator.__init__, base_classes.py:504-510). */
+/* params: F110_NUM_PARAMS doubles applied to every agent (Simulator.__init__, base_classes.py:504-510).
+ * Environment switches read here (development / test aids, none changes a result):
+ *   F110_DEBUG_SYNC=1   synchronise after every kernel of a step and name the one that faulted
+ *   F110_LIDAR_TILE=1   single-agent handles run the shared-memory tile experiment of the lidar kernel
+ * and by f110_set_map_image:
+ *   F110_EDT_WIDE=1     force the general form of the device EDT on a map the 16-bit form would take */
 int f110_create(const F110Config* cfg, const double* params, F110Sim** out);
 void f110_destroy(F110Sim* sim);
 
