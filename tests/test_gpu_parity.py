@@ -1095,9 +1095,12 @@ def test_c4_full_size_sharded_properties():
     sim.close()
 
 
-def test_shaped_reward_kernel_matches_reference_and_oracle():
+@pytest.mark.parametrize('form', ['warp', 'cta'])
+def test_shaped_reward_kernel_matches_reference_and_oracle(form, monkeypatch):
     """f110_reward_compute: (a) the recorded reference episodes, each replayed in its own env slot of one batch, (b) the
-    oracle on a seeded batch of independent envs.  Tolerance 1e-9 (fp64, device libm); crash returns are exact."""
+    oracle on a seeded batch of independent envs.  Tolerance 1e-9 (fp64, device libm); crash returns are exact.  Both
+    forms of the kernel: a warp per env (the default) and a CTA per env (scans too long for a warp's shared memory; forced)."""
+    monkeypatch.setenv('F110_REWARD_CTA', '1' if form == 'cta' else '0')
     torch = _torch()
     from f110_gymnasium_ros2_jazzy_b200 import ShapedReward
     from oracle.f110_oracle import RewardOracle
