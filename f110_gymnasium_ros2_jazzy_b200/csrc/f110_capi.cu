@@ -149,9 +149,15 @@ int run_step(F110Sim* sim, const F110StepIO& io, cudaStream_t s) {
         for (int i = 0; i < 4; ++i) { CUDA_TRY(cudaEventCreate(&e[i])); sim->tev.push_back(e[i]); }
         CUDA_TRY(cudaEventRecord(e[0], s));
     }
-    // F110_DEBUG_SYNC=1 in the environment: wait for each kernel and name the one that faulted
+    // F110_DEBUG_SYNC=1 in the environment: wait for each kernel and name the one that faulted (not while the stream is
+    // being captured into a CUDA graph, where a synchronisation is illegal)
+    bool dbg = sim->debug_sync;
+    if (dbg) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) dbg = false;
+    }
 #define DEBUG_SYNC(name)                                                                                           \
-    if (sim->debug_sync) {                                                                                         \
+    if (dbg) {                                                                                                     \
         const cudaError_t de = cudaStreamSynchronize(s);                                                           \
         if (de != cudaSuccess) return fail(F110_ERR_CUDA, "%s: %s", name, cudaGetErrorString(de));                 \
     }
