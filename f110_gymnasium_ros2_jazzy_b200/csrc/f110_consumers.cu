@@ -636,16 +636,18 @@ __global__ void __launch_bounds__(RWW_MAX * 32) shaped_reward_warp_kernel(Reward
     int* s_cblk = reinterpret_cast<int*>(s_hist + 256);                   // [256]
     int* s_knn = s_cblk + 256;                                            // [2][KNN]
     const float* ob = obs + (size_t)env * (B + 8);
-    RewardState& r = v.st[env];
+    // the env's progress state lives in lane 0's registers for the duration of the kernel: one load of the record and one
+    // store, instead of a dependent global access per field of the state machine
+    RewardState r;
+    memset(&r, 0, sizeof(r));
 
     double pose[5] = {0., 0., 0., 0., 0.};                                // ex, ey, ox, oy, oth
     int early = 0, steps = 0, do_wall = 0;
     if (lane == 0) {
         if (reset_mask && reset_mask[env]) {        // reward_fn.reset() (rewards.py:262-264, _Prog.reset :98-106)
-            RewardState z;
-            memset(&z, 0, sizeof(z));
-            z.flip = +1.0;
-            r = z;
+            r.flip = +1.0;                          // everything else zero
+        } else {
+            r = v.st[env];
         }
         // parse_flat_obs :11-39 (the float32 fields are widened by float())
         pose[0] = (double)ob[B + 0]; pose[1] = (double)ob[B + 1];
@@ -660,6 +662,7 @@ __global__ void __launch_bounds__(RWW_MAX * 32) shaped_reward_warp_kernel(Reward
         if (ego_col) { early = 1; if (out64) out64[env] = -v.p.ego_crash_penalty; if (out32) out32[env] = (float)-v.p.ego_crash_penalty; }
         else if (opp_col && v.p.opp_crash_bonus > 0.0) { early = 1; if (out64) out64[env] = v.p.opp_crash_bonus; if (out32) out32[env] = (float)v.p.opp_crash_bonus; }
         do_wall = r.steps >= v.p.grace_steps_wall;
+        if (early) v.st[env] = r;
     }
     early = __shfl_sync(0xffffffffu, early, 0);
     if (early) return;
@@ -860,6 +863,7 @@ __global__ void __launch_bounds__(RWW_MAX * 32) shaped_reward_warp_kernel(Reward
         const double total = r_prog + r_alive + r_lead + r_lat + r_wall + r_opp + r_flank;
         if (out64) out64[env] = total;
         if (out32) out32[env] = (float)total;
+        v.st[env] = r;
     }
 }
 
