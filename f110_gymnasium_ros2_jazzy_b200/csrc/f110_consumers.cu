@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gap_follow_kernel(const float* 
     unsigned* words = reinterpret_cast<unsigned*>(proc + n);     // [groups]: bit b of word k = beam 32 k + b is above the threshold
     const float* scan = scans + (size_t)scan_id * scan_stride;
 
-    // the scan comes from DRAM (the lidar kernel wrote it with streaming stores): eight loads in flight per lane -- one
+    // the scan comes from DRAM (the lidar kernel wrote it with streaming stores): seventeen loads in flight per lane -- one
     // at a time, a warp waited 34 DRAM round trips in a row and the kernel ran at a ninth of the memory's speed
-    constexpr int U = 8;
+    constexpr int U = 17;     // 1080 beams = two batches
     for (int base = 0; base < n; base += 32 * U) {
         float v[U];
 #pragma unroll
