@@ -25,7 +25,7 @@ F110_ERR_POSE_COUNT, F110_ERR_INTEGRATOR, F110_ERR_NO_DEVICE = -5, -6, -7
 EXPORTS = ["f110_last_error", "f110_abi_version", "f110_create", "f110_destroy", "f110_set_map", "f110_set_map_image", "f110_get_map", "f110_set_tables",
            "f110_set_beam_tables", "f110_set_params", "f110_sim_reset", "f110_sim_reset_host", "f110_step", "f110_step_host", "f110_step_host_async", "f110_host_sync", "f110_step_host_multi",
            "f110_state_nbytes", "f110_get_state", "f110_set_state", "f110_get_stats", "f110_get_lookup_count",
-           "f110_kernel_launches", "f110_set_lidar_wave", "f110_max_lookups", "f110_redone_rays", "f110_map_generation", "f110_debug_unit_timeline", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_edt_kernel_ms", "f110_reward_create", "f110_reward_destroy",
+           "f110_kernel_launches", "f110_max_lookups", "f110_redone_rays", "f110_map_generation", "f110_debug_unit_timeline", "f110_set_kernel_timing", "f110_get_kernel_timing", "f110_gap_follow", "f110_gather_probe", "f110_edt_kernel_ms", "f110_reward_create", "f110_reward_destroy",
            "f110_reward_compute"]
 
 
@@ -93,7 +93,6 @@ def load():
     L.f110_get_stats.argtypes = [vp, vp, C.c_int32, vp]
     L.f110_get_lookup_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.f110_set_kernel_timing.argtypes = [vp, C.c_int32]
-    L.f110_set_lidar_wave.argtypes = [vp, C.c_int32]
     L.f110_get_kernel_timing.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     L.f110_gap_follow.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, C.c_double, C.c_double, C.c_float,
                                   C.c_int32, C.c_int32, C.c_float, vp]

@@ -331,11 +331,6 @@ class BatchSim(object):
         self.redone_rays = int(self.lib.f110_redone_rays(self.h))
         return a.value, b.value
 
-    def set_lidar_wave(self, percent):
-        """This handle's lidar launches use `percent` of the resident wave of persistent warps, leaving the rest of the
-        machine to handles stepped beside it on other streams (include/f110_b200.h, f110_set_lidar_wave)."""
-        _lib.check(self.lib.f110_set_lidar_wave(self.h, int(percent)))
-
     @property
     def kernel_launches(self):
         return int(self.lib.f110_kernel_launches(self.h))

@@ -79,7 +79,6 @@ struct F110Sim {
     unsigned long long max_lookups = 0;   // longest ray (lookups) seen, refreshed by f110_get_lookup_count
     unsigned long long redone_rays = 0;   // rays the lidar kernel redid in exact arithmetic, refreshed likewise
     int lidar_blocks = 0;         // CTAs of one resident wave of the lidar kernel (persistent warps)
-    int lidar_blocks_full = 0;    // the whole wave (lidar_blocks is a share of it after f110_set_lidar_wave)
     std::vector<cudaEvent_t> tev;   // 4 events per timed step
     uint64_t ckpt_header_words[8] = {0};   // host staging of the checkpoint header (see f110_get_state)
     EdtScratch edt;               // f110_set_map_image's device scratch, kept between calls
@@ -214,7 +213,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     sim->narrow_fraction = (cfg->flags & F110_FLAG_NARROW_FRACTION) != 0;
     sim->debug_sync = getenv("F110_DEBUG_SYNC") != nullptr;
     { const char* t = getenv("F110_LIDAR_TILE"); sim->lidar_tile = t && t[0] == '1'; }
-    sim->lidar_blocks = sim->lidar_blocks_full = lidar_resident_blocks(A == 1);
+    sim->lidar_blocks = lidar_resident_blocks(A == 1);
     sim->sc.ordered = 0;   // set below, once the unit count is known
     if (sim->lidar_blocks < 1) {
         cudaGetLastError();
@@ -727,12 +726,5 @@ int64_t f110_redone_rays(const F110Sim* sim) { return sim ? (int64_t)sim->redone
 int64_t f110_map_generation(const F110Sim* sim) { return sim ? sim->map_generation : 0; }
 
 int64_t f110_kernel_launches(const F110Sim* sim) { return sim ? sim->launches : 0; }
-
-int f110_set_lidar_wave(F110Sim* sim, int32_t percent) {
-    if (!sim || percent < 1 || percent > 100) return fail(F110_ERR_INVALID, "f110_set_lidar_wave: percent must be in [1, 100]");
-    const long long blocks = ((long long)sim->lidar_blocks_full * percent + 99) / 100;
-    sim->lidar_blocks = (int)(blocks < 1 ? 1 : blocks);
-    return F110_OK;
-}
 
 }  // extern "C"

@@ -335,7 +335,7 @@ class F110HostVecEnv(object):
     """
 
     def __init__(self, num_envs, chunks=2, map_arrays=None, map_dir=None, map=None, map_ext='.png', num_agents=1,
-                 seed=42, device=None, outputs=FAST_OUTPUTS, num_beams=1080, wave=None, **kw):
+                 seed=42, device=None, outputs=FAST_OUTPUTS, num_beams=1080, **kw):
         self.num_envs, self.num_agents, self.num_beams = num_envs, num_agents, num_beams
         if isinstance(chunks, int):
             chunks = max(1, min(chunks, num_envs))
@@ -353,8 +353,6 @@ class F110HostVecEnv(object):
                 b.set_map_arrays(*map_arrays)
             else:
                 b.set_map(map_dir + map + '.yaml', map_ext)
-            if wave is not None and wave[k] is not None:
-                b.set_lidar_wave(wave[k])
             self.parts.append(b)
         outs = tuple(dict.fromkeys(tuple(outputs) + ('obs', 'reward', 'terminated')))
         from .backend import _OUT_SPECS

@@ -226,12 +226,6 @@ int f110_get_kernel_timing(F110Sim* sim, double* ms3, int64_t* steps);
 /* Launch bookkeeping for bench.py: kernels launched by this handle since creation. */
 int64_t f110_kernel_launches(const F110Sim* sim);
 
-/* The lidar kernel is one resident wave of persistent warps that take 32-beam units from a queue.  A caller that steps
- * several handles at once on their own streams (f110_step_host_multi: env chunks whose downloads overlap the other
- * chunks' kernels) can leave room for the others: this handle's lidar launches then use `percent` (1..100) of the
- * wave.  Results do not depend on it (only which warp marches which unit does).  No reference counterpart. */
-int f110_set_lidar_wave(F110Sim* sim, int32_t percent);
-
 /* ---- consumers around the env, on the device ----
  * gap_follow_action (rl_training/utils/gap_follow.py:43-58), the rule-based opponent train_ddpg.py:168 drives from
  * info["scans"][1]: for scan k (DEVICE float[num_beams] at scans + k*scan_stride) writes (steer, speed) as two floats
