@@ -104,7 +104,7 @@ void layout_scratch(Arena& a, StepScratch& sc, int NA, int B, bool timeline) {
     sc.ttc_hit = a.take<int32_t>(NA);
     sc.lookups = a.take<unsigned long long>(4);
     sc.stats = a.take<double>(F110_NUM_STATS);
-    sc.num_units = (unsigned)((size_t)NA * ((B + LIDAR_UNIT - 1) / LIDAR_UNIT));
+    sc.num_units = (unsigned)((size_t)NA * ((B + 31) / 32));
     // capacities of the three heavy-unit lists (classes >= 96 / 48 / 24 lookups); a list that overflows sends the rest of
     // its class to the light region, which costs order, never correctness
     sc.cap[0] = sc.num_units / 16 + 8; sc.cap[1] = sc.num_units / 8 + 8; sc.cap[2] = sc.num_units / 4 + 8;
@@ -275,7 +275,7 @@ int f110_create(const F110Config* cfg, const double* params, F110Sim** out) {
     c.lidar_max = (float)cfg->lidar_max; c.seed = cfg->seed;
     c.noise_key = (uint32_t)cfg->seed ^ ((uint32_t)(cfg->seed >> 32) * 0x85EBCA6Bu) ^ 0x46313130u;
     c.div_B = make_fast_div((uint32_t)B); c.div_A = make_fast_div((uint32_t)A);
-    c.ups = (unsigned)((B + LIDAR_UNIT - 1) / LIDAR_UNIT); c.div_ups = make_fast_div(c.ups);
+    c.ups = (unsigned)((B + 31) / 32); c.div_ups = make_fast_div(c.ups);
     for (int r = 0; r < 10; ++r) c.philox_key[r] = c.noise_key + (uint32_t)r * 0x9E3779B9u;
     c.obs_rcp = 1.0f / c.lidar_max;
     c.obs_fast_div = c.lidar_max == 30.0f ? 1 : 0;

@@ -569,134 +569,6 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
         if (!skip) {
             unsigned t_start = 0;
             if (COUNT) asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_start));
-#if LIDAR_RPL == 2
-            // ---- two adjacent beams per lane (a unit is 64 beams): their marches run in lockstep, so a warp has twice the
-            // loads in flight and pays the unit's fixed part (queue, scan head, history) once per 64 rays
-            const unsigned s = fast_div(unit, c.div_ups);
-            const unsigned i0 = (unit - s * c.ups) * 64u + 2u * lane;
-            const unsigned env = DIRECT ? s : fast_div(s, c.div_A);
-            const bool act = LEAN || !(io.active_mask && !io.active_mask[env]);
-            const bool live0 = i0 < (unsigned)c.B && act, live1 = i0 + 1u < (unsigned)c.B && act;
-            live = live0;
-            const double4 head = reinterpret_cast<const double4*>(sc.head)[s];
-            const unsigned stepc = st.step_count[env];
-            const double td = (double)c.theta_dis;
-            int ti[2];
-            double2 dir[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const unsigned i = i0 + (unsigned)r;
-                const unsigned ic = i < (unsigned)c.B ? i : (unsigned)c.B - 1u;
-                double t = head.z + (double)ic * c.theta_inc;
-                if (t >= td) t -= td;
-                if (fabs(t - rint(t)) < 1e-9 || t >= td) {
-                    t = head.z;
-                    for (unsigned k = 0; k < ic; ++k) {
-                        t += c.theta_inc;
-                        while (t >= td) t -= td;
-                    }
-                }
-                int tr = (int)t;
-                tr = (unsigned)tr < (unsigned)c.theta_dis ? tr : c.theta_dis - 1;
-                ti[r] = tr;
-                dir[r] = __ldg(c.dir_fx + tr);
-            }
-            const double ttc_lim = head.w;
-            const unsigned rid = s * (unsigned)(c.B + 8) + i0;
-
-            double tot[2] = {0.0, 0.0}, dend[2] = {0.0, 0.0};
-            unsigned nl[2] = {0u, 0u};
-            {
-                const unsigned fb = TUNED ? (unsigned)FB : m.fx_bits;
-                const unsigned gm = TUNED ? (((1u << FB) - 1u) & ~3u) : m.guard_mask;
-                const int pitch = TUNED ? (1 << (32 - FB)) + 16 : m.pitch;
-                const double eps = c.eps;
-                const double max_range = TUNED ? 30.0 : c.max_range;
-                const double* __restrict__ dt = m.dt;
-                double X0 = head.x, Y0 = head.y, X1 = head.x, Y1 = head.y;
-                unsigned ux = __double2uint_rz(X0), uy = __double2uint_rz(Y0);
-                unsigned tx, ty;
-                asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));
-                asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
-                const bool dec_init = tx != 0u && ty != 0u;      // both rays start in the same cell
-                bool g0 = live0 && dec_init, g1 = live1 && dec_init;
-                const bool started0 = g0, started1 = g1;
-                double da0 = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb))), db0 = 0.0;
-                double da1 = da0, db1 = 0.0;
-                unsigned trips = 0;
-                bool ok;
-#define F110_MARCH_STEP2(R, D_CUR, D_NEXT)                                                                     \
-                    X##R += D_CUR * dir[R].x;                                                                  \
-                    Y##R += D_CUR * dir[R].y;                                                                  \
-                    ux = __double2uint_rz(X##R);                                                               \
-                    uy = __double2uint_rz(Y##R);                                                               \
-                    D_NEXT = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));                          \
-                    tot[R] += D_CUR;                                                                           \
-                    asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));                        \
-                    asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));                        \
-                    ok = (TUNED ? D_CUR > 0.0 : D_CUR > eps) && tot[R] <= max_range && tx != 0u && ty != 0u;
-                if (g0 || g1) for (;;) {
-                    if (g0) { F110_MARCH_STEP2(0, da0, db0) if (!ok) { g0 = false; nl[0] = 2u * trips + 1u; dend[0] = da0; } }
-                    if (g1) { F110_MARCH_STEP2(1, da1, db1) if (!ok) { g1 = false; nl[1] = 2u * trips + 1u; dend[1] = da1; } }
-                    if (!(g0 || g1)) break;
-                    if (g0) { F110_MARCH_STEP2(0, db0, da0) if (!ok) { g0 = false; nl[0] = 2u * trips + 2u; dend[0] = db0; } }
-                    if (g1) { F110_MARCH_STEP2(1, db1, da1) if (!ok) { g1 = false; nl[1] = 2u * trips + 2u; dend[1] = db1; } }
-                    if (!(g0 || g1)) break;
-                    ++trips;
-                }
-#undef F110_MARCH_STEP2
-                const bool lv[2] = {live0, live1}, started[2] = {started0, started1};
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    // ended on a lookup (dend is its last cell: a sentinel means it left the map), or goes on and the lookup
-                    // after it could not be decided; a ray that never started was undecided at its first lookup
-                    const bool decided = started[r] && !((TUNED ? dend[r] > 0.0 : dend[r] > eps) && tot[r] <= max_range);
-                    if (lv[r] && (!decided || dend[r] < 0.0)) {
-                        const double2 ex = trace_ray_exact(m, c, sc, s, ti[r]);
-                        tot[r] = ex.x;
-                        nl[r] = (unsigned)ex.y;
-                        if (COUNT) { ++cnt_redone; redone_here = true; }
-                    }
-                    if (tot[r] > c.max_range) tot[r] = c.max_range;
-                }
-            }
-            nlook = max(nl[0], nl[1]);
-
-            npos_next = pos + 1u;
-            const bool chunk_end = npos_next >= end;
-            if (chunk_end) fetch(pos);
-            else resolve(npos_next, nunit, nskip);
-
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (r == 0 ? live0 : live1) {
-                    const unsigned ridr = rid + (unsigned)r;
-                    const unsigned q = OBS_ONLY ? 0u : ridr - 8u * s;      // s * B + i: the ray's element of the scan outputs
-                    double range = tot[r];
-                    if (!LEAN && io.noise) {
-                        range += io.noise[q];
-                    } else if (c.noise_std > 0.0) {
-                        const uint2 bits = philox2x32_10(make_uint2(ridr, stepc), c.philox_key);
-                        range += c.noise_std * (double)gaussian_from_bits(bits.x, bits.y);
-                    }
-                    if (!LEAN && io.scans_f64) __stcs(io.scans_f64 + q, range);
-                    if (!OBS_ONLY && io.scans_f32) __stcs(io.scans_f32 + q, (float)range);
-                    if (DIRECT) {
-                        if (OBS_ONLY || io.obs) __stcs(io.obs + ridr, obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
-                    } else {
-                        if (io.obs && s == env * (unsigned)c.A)
-                            __stcs(io.obs + (env * (unsigned)(c.B + 8) + i0 + (unsigned)r), obs_lidar<TUNED>(range, c.lidar_max, c.obs_rcp));
-                    }
-                    if (!(range > ttc_lim)) {
-                        const unsigned s2 = fast_div(unit, c.div_ups), i2 = (unit - s2 * c.ups) * 64u + 2u * lane + (unsigned)r;
-                        const double2 bt2 = __ldg(c.beam_tt + i2);       // beam cosine, side distance
-                        const double ttc = (range - bt2.y) / (st.x[3][s2] * bt2.x);
-                        if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s2] = 1;
-                    }
-                }
-            }
-            if (COUNT) { cnt_look += min(nl[0], nl[1]); cnt_rays += live1 ? 1u : 0u; }   // the rest is added below (nlook = the larger)
-#else
             // ---- the unit's scan and this lane's beam
             const unsigned s = fast_div(unit, c.div_ups);
             const unsigned i = (unit - s * c.ups) * 32u + lane;
@@ -834,7 +706,6 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                     if ((ttc < c.ttc_thresh) && (ttc >= 0.0)) sc.ttc_hit[s2] = 1;
                 }
             }
-#endif
             // ---- history for the next step's launch order.  The class goes to the unit AND its two neighbours in the scan: a
             // long (wall-grazing) ray wanders across the beam index as the car yaws, and the unit it moves into has no
             // history of its own -- 22 units per step with >= 48 lookups were predicted light, the longest ~120 lookups;
@@ -1667,7 +1538,7 @@ cudaError_t launch_lidar(const SimConst& c, const MapView& m, const SimState& st
     // TUNED variant: compile-time fraction bits, d > 0 for d > eps, max_range 30, the observation's division by 30 through its reciprocal
     const bool tuned = m.guard == 2u && c.obs_fast_div && c.max_range == 30.0 && c.eps > 0.0 && m.min_positive > c.eps &&
                        m.fx_bits >= 19u && m.fx_bits <= 22u;
-    if (tile_experiment && LIDAR_RPL == 1 && tuned && c.A == 1 && !count_lookups) {
+    if (tile_experiment && tuned && c.A == 1 && !count_lookups) {
         LidarTileKernel k = m.fx_bits == 19u ? lidar_tile_kernel<19> : m.fx_bits == 20u ? lidar_tile_kernel<20> :
                             m.fx_bits == 21u ? lidar_tile_kernel<21> : lidar_tile_kernel<22>;
         int dev = 0, sms = 148;

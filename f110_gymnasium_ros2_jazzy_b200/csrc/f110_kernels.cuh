@@ -80,12 +80,6 @@ struct StepScratch {
                                //   processed, alternating every second step (see lidar_kernel)
 };
 // the four words atomics hit (queue position, the three counts being recorded) sit on 128-byte lines of their own
-// Beams per lane in the lidar kernel (1 or 2); a unit is 32 * LIDAR_RPL consecutive beams of one scan.
-#ifndef LIDAR_RPL
-#define LIDAR_RPL 1
-#endif
-constexpr unsigned LIDAR_UNIT = 32u * LIDAR_RPL;
-
 enum { CTRL_POS = 0, CTRL_NEXT = 32, CTRL_NEXT_STRIDE = 32, CTRL_EPOCH = 128, CTRL_CUR = 129, F110_CTRL_WORDS = 160 };
 
 struct FastDiv { uint32_t mul, sh1, sh2; };   // n / d == (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(n, mul)
