@@ -457,12 +457,6 @@ constexpr int LIDAR_THREADS = LIDAR_THREADS_OVERRIDE;
 #ifndef LIDAR_LIST2_TAKE
 #define LIDAR_LIST2_TAKE 2u    // positions per fetch in the third (lightest) heavy list (1 in the two heavier ones)
 #endif
-#ifndef LIDAR_COOP_SPACING
-#define LIDAR_COOP_SPACING 1.0   // cell lengths between the cells touched along the leading ray (LIDAR_COOP builds)
-#endif
-#ifndef LIDAR_COOP_LD
-#define LIDAR_COOP_LD 0          // 1: touch by a discarded load instead of prefetch.global.L1
-#endif
 #ifndef LIDAR_MIN_TAKE
 #define LIDAR_MIN_TAKE 2u     // positions per fetch in the last stretch of the light region (see `fetch`)
 #endif
@@ -622,71 +616,6 @@ lidar_kernel(const __grid_constant__ SimConst c, const __grid_constant__ MapView
                 // load; the range / eps / guard tests run beside the load instead of in front of it.  Cost: one extra
                 // lookup per ray.
                 bool decided = true;
-#ifdef LIDAR_COOP
-                // A unit from one of the heavy lists (warp-uniform): its long rays creep along a wall, every lookup an L2
-                // round trip on the dependent chain.  The march runs in rounds of LIDAR_COOP trips; between rounds the lanes
-                // -- most of whose own rays have ended -- touch the cells along the line of the lowest lane still marching
-                // (one cell length apart, the next 32), so that its lookups, and those of the neighbouring beams that graze
-                // the same wall, find their sectors in L1.  Only latency changes: no value read differs.
-                const bool coop = pos < n2;
-                if (coop) {
-                    bool going = false, second = false;
-                    unsigned trips = 0, tx, ty;
-                    double da = 0.0, db = 0.0;
-                    if (live) {
-                        unsigned ux = __double2uint_rz(X), uy = __double2uint_rz(Y);
-                        asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));
-                        asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
-                        decided = tx != 0u && ty != 0u;
-                        if (decided) { da = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb))); going = true; }
-                    }
-                    const bool started = going;
-                    for (unsigned round = 0;; ++round) {
-                        const unsigned cont = __ballot_sync(0xffffffffu, going);
-                        if (cont == 0u) break;
-                        if (round != 0u) {
-                            const int lead = __ffs((int)cont) - 1;
-                            const double lx = __shfl_sync(0xffffffffu, X, lead), ly = __shfl_sync(0xffffffffu, Y, lead);
-                            const double ldx = __shfl_sync(0xffffffffu, dir.x, lead), ldy = __shfl_sync(0xffffffffu, dir.y, lead);
-                            const double t = (double)(lane + 1u) * (LIDAR_COOP_SPACING * m.res);
-                            const unsigned px = __double2uint_rz(lx + t * ldx), py = __double2uint_rz(ly + t * ldy);
-                            const double* cell = dt + ((int)(py >> fb) * pitch + (int)(px >> fb));
-#if LIDAR_COOP_LD
-                            double sink;
-                            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(sink) : "l"(cell));
-#else
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(cell));
-#endif
-                        }
-                        if (going) {
-                            unsigned ux, uy, t = 0;
-#define F110_MARCH_STEP(D_CUR, D_NEXT)                                                                         \
-                            X += D_CUR * dir.x;                                                                \
-                            Y += D_CUR * dir.y;                                                                \
-                            ux = __double2uint_rz(X);                                                          \
-                            uy = __double2uint_rz(Y);                                                          \
-                            D_NEXT = __ldg(dt + ((int)(uy >> fb) * pitch + (int)(ux >> fb)));                  \
-                            total_d += D_CUR;                                                                  \
-                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(tx) : "r"(ux), "r"(gm));                \
-                            asm("lop3.b32 %0, %1, %2, 0, 0x0c;" : "=r"(ty) : "r"(uy), "r"(gm));
-                            for (;;) {
-                                F110_MARCH_STEP(da, db)
-                                if (!((TUNED ? da > 0.0 : da > eps) && total_d <= max_range && tx != 0u && ty != 0u)) { going = false; break; }
-                                F110_MARCH_STEP(db, da)
-                                if (!((TUNED ? db > 0.0 : db > eps) && total_d <= max_range && tx != 0u && ty != 0u)) { going = false; second = true; break; }
-                                ++trips;
-                                if (++t == LIDAR_COOP) break;
-                            }
-#undef F110_MARCH_STEP
-                        }
-                    }
-                    if (started) {
-                        d = second ? db : da;
-                        nlook = 2u * trips + (second ? 2u : 1u);
-                        decided = !((TUNED ? d > 0.0 : d > eps) && total_d <= max_range);
-                    }
-                } else
-#endif
                 if (live) {
                     unsigned ux = __double2uint_rz(X), uy = __double2uint_rz(Y);
                     unsigned tx, ty;
