@@ -9,6 +9,7 @@ N = 4096
 poses = cl[np.linspace(0, len(cl) - 1, N).round().astype(int)][:, None, :]
 acts = torch.rand((120, N, 1, 2)).mul(torch.tensor([0.8, 20.])).sub(torch.tensor([0.4, 0.])).pin_memory().numpy()
 SETS = {'r01': (1, 2, 3, 4, (1, 3), (1, 2), (1, 2, 3), (1, 2, 2), (1, 3, 4), (2, 3, 3), (1, 1, 2, 4), (1, 2, 3, 4), (3, 2)),
+        'quick': ((1, 3), (1, 4), (1, 2), 2, (1, 1, 2), (1, 2, 5), (1, 3)),
         'two': ((1, 3), (1, 4), (1, 5), (1, 7), (1, 9), (1, 11), (1, 15), (1, 31), (1, 3), (1, 5, 10))}
 for chunks in SETS[sys.argv[1] if len(sys.argv) > 1 else 'r01']:
     env = F110HostVecEnv(N, chunks=chunks, map_arrays=m, num_agents=1)
