@@ -635,6 +635,33 @@ def test_device_noise_statistics():
     assert 2.8 < k < 3.2
 
 
+def test_device_noise_law_and_stream_semantics():
+    """The on-device noise stream beyond its first two moments: Kolmogorov-Smirnov against N(0, 0.01^2) over 1.1e6 rays,
+    the Box-Muller tail (u1 has 24 bits: |z| <= sqrt(50 ln 2) = 5.89), no correlation between neighbouring beams, between
+    consecutive steps of the same ray or between envs, and the reference's episode semantics -- RaceCar.reset re-seeds the
+    generator (base_classes.py:204), so every reset replays the same noise."""
+    from scipy import stats
+    N = 512
+    be = GpuBackend(N, 1, 'open_square', noise_std=0.01, seed=11)
+    ref = GpuBackend(1, 1, 'open_square')                     # the same env without noise: every env of `be` is this one
+    poses = np.zeros((N, 1, 3))
+    zero, none = np.zeros((N, 1, 2), np.float32), np.zeros((1, 1, 1080))
+    clean = [ref.reset(poses[:1], none)['scans'][0, 0]] + [ref.step(zero[:1], none)['scans'][0, 0].copy() for _ in range(2)]
+    noisy = [be.reset(poses, None)['scans'][:, 0]] + [be.step(zero, None)['scans'][:, 0].copy() for _ in range(2)]
+    first, second, third = (n - c[None] for n, c in zip(noisy, clean))
+    z = np.concatenate([first.ravel(), second.ravel()]) / 0.01
+    d, _ = stats.kstest(z, 'norm')
+    assert d < 0.004, d                                        # 1.1e6 samples: the 0.1 % critical value is 0.0019
+    assert 4.0 < np.abs(z).max() < 5.95
+    rho = lambda a, b: abs(np.corrcoef(a.ravel(), b.ravel())[0, 1])
+    assert rho(first[:, :-1], first[:, 1:]) < 0.008            # neighbouring beams (5.5e5 pairs: sigma = 0.0013)
+    assert rho(first, second) < 0.008 and rho(second, third) < 0.008       # the same ray, consecutive steps
+    assert rho(first[:-1], first[1:]) < 0.008                  # the same ray of neighbouring envs
+    again = be.reset(poses, None)['scans'][:, 0]
+    assert np.array_equal(again, noisy[0])                     # a reset restarts the stream
+    assert np.array_equal(be.step(zero, None)['scans'][:, 0], noisy[1])
+
+
 def test_env_api_matches_reference_surface(tmp_path):
     """F110Env drop-in: kwargs, return types, info keys/dtypes (f110_env.py:586-602) and the golden rollout."""
     _torch()
